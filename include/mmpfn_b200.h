@@ -1,0 +1,187 @@
+/*
+ * mmpfn_b200.h — C ABI of libmmpfn_b200.so: the sm_100a implementation of MMPFN's in-context
+ * inference hot path (TabPFN-v2 PerFeatureTransformer forward + image/text token stem).
+ *
+ * The reference is pure Python/PyTorch and has no FFI of its own; the boundary this library
+ * replaces is the model call of the inference engine,
+ *     mmpfn/models/mmpfn/inference.py:343-348   self.model(None, X_full, image_full, y_train, ...)
+ * i.e. PerFeatureTransformer._forward (mmpfn/models/mmpfn/model/transformer.py:555-867), plus the
+ * probability tail of MMPFNClassifier.predict_proba (mmpfn/models/mmpfn/classifier.py:544-576).
+ * Each entry point below cites the reference lines whose work it performs.  INTEGRATION.md shows
+ * the ctypes binding a maintainer of the reference would add.
+ *
+ * Conventions
+ *  - every pointer is a DEVICE pointer unless the name ends in _host; buffers are owned by the
+ *    caller (torch allocates them); nothing is allocated or freed inside the library;
+ *  - every call is asynchronous on `stream` (a cudaStream_t passed as void*), performs no host
+ *    synchronisation, and returns 0 on success or a negative MMPFN_E* code; mmpfn_last_error()
+ *    returns a thread-local message for the last failure;
+ *  - there is NO CPU fallback: on a machine without an sm_100 device every compute entry point
+ *    returns MMPFN_ENODEVICE;
+ *  - tensors are dense, row-major, innermost dimension last, in the layouts stated per call;
+ *  - `precision`: MMPFN_F32 (FFMA kernels, the 1e-5 parity mode) or MMPFN_BF16 (tcgen05/TMEM/TMA
+ *    kernels: bf16 MMA operands, fp32 accumulation, fp32 softmax/LayerNorm statistics and an fp32
+ *    residual stream).
+ */
+#ifndef MMPFN_B200_H
+#define MMPFN_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define MMPFN_ABI_VERSION 1
+
+enum { MMPFN_OK = 0, MMPFN_EINVAL = -1, MMPFN_ENODEVICE = -2, MMPFN_ECUDA = -3, MMPFN_EUNSUPPORTED = -4 };
+enum { MMPFN_F32 = 0, MMPFN_BF16 = 1 };
+enum { MMPFN_MIXER_NONE = 0, MMPFN_MIXER_MGM = 1, MMPFN_MIXER_MGM_CAP = 2, MMPFN_MIXER_MOE = 3 };
+
+/* Geometry of the checkpoint (reference model/config.py:18-83, model/loading.py:470-538).
+ * Supported: emsize 192, nhead 6 (d_k 32), nhid 768, features_per_group 1 or 2. */
+typedef struct mmpfn_geometry {
+  int32_t emsize, nhead, nhid, nlayers, n_out, features_per_group;
+  int32_t img_dim, mgm_heads, cap_heads, mixer_type;
+} mmpfn_geometry;
+
+/* Repacked weights (device pointers).  Layouts are produced by multimodalpfn_b200/weights.py from a
+ * reference state_dict.  All matrices are "W[N][K]" (output-major), so a
+ * projection is out[n] = sum_k in[k] * W[n][k].
+ *
+ * layers_f32 / layers_bf16: nlayers consecutive blocks of
+ *     feat_wqkv [3*E][E] | feat_wout [E][E] | item_wqkv [3*E][E] | item_wout [E][E]
+ *     | mlp_w1 [nhid][E] | mlp_w2 [E][nhid]
+ * where wqkv rows are ordered (j in q,k,v; head; d) exactly like the reference `_w_qkv [3,H,D,E]`
+ * (model/multi_head_attention.py:216-260) and wout[e][h*D+d] = reference `_w_out[h][d][e]`. */
+typedef struct mmpfn_weights {
+  const float*    layers_f32;
+  const uint16_t* layers_bf16;      /* may be NULL when only MMPFN_F32 is used */
+  const float* enc_w;               /* [E][2*fpg]   encoder.5.layer.weight (no bias) */
+  const float* yenc_w;              /* [E][2]       y_encoder.2.layer.weight */
+  const float* yenc_b;              /* [E] */
+  const float* dec_w1;              /* [nhid][E]    decoder_dict.standard.0 */
+  const float* dec_b1;              /* [nhid] */
+  const float* dec_w2;              /* [n_out][nhid] decoder_dict.standard.2 */
+  const float* dec_b2;              /* [n_out] */
+  /* image / text stem; NULL when mixer_type == MMPFN_MIXER_NONE */
+  const float* mgm_w1;              /* [Hm*img][img]  LN affine folded in; GLU halves interleaved:
+                                       row h*img + 2*c = value c, row h*img + 2*c+1 = gate c
+                                       (MoE: [Hm*img/2][img], plain order) */
+  const float* mgm_b1;              /* [Hm*img]       (MoE: [Hm*img/2]) */
+  const float* mgm_w2;              /* [Hm][E][img/2] */
+  const float* mgm_b2;              /* [Hm][E] */
+  const float* moe_gate_w;          /* [Hm][img]   MoE only */
+  const float* moe_gate_b;          /* [Hm] */
+  const float* cap_knorm_w;         /* [E] */
+  const float* cap_knorm_b;         /* [E] */
+  const float* cap_q;               /* [Hc][E]  in_proj_q(q_proj(q_norm(queries))) precomputed (row independent) */
+  const float* cap_wkv;             /* [2*E][E] in_proj rows E..3E */
+  const float* cap_bkv;             /* [2*E] */
+  const float* cap_wo;              /* [E][E] */
+  const float* cap_bo;              /* [E] */
+  const float* cap_onorm_w;         /* [E] */
+  const float* cap_onorm_b;         /* [E] */
+  const float* cap_f1_w;            /* [2E][E] */
+  const float* cap_f1_b;            /* [2E] */
+  const float* cap_f2_w;            /* [E][2E] */
+  const float* cap_f2_b;            /* [E] */
+} mmpfn_weights;
+
+/* ---- introspection ------------------------------------------------------------------------- */
+int         mmpfn_abi_version(void);
+const char* mmpfn_last_error(void);
+/* number of kernels this library has launched in the calling process (bench `gpu_launches`) */
+int64_t     mmpfn_launch_count(void);
+/* 1 if device `dev` is an sm_100 part this library can run on */
+int         mmpfn_device_supported(int dev);
+
+/* floats per layer block in mmpfn_weights.layers_* */
+size_t mmpfn_layer_weight_elems(const mmpfn_geometry* g);
+
+/* ---- stem ---------------------------------------------------------------------------------- */
+/* Number of image tokens the mixer emits per row (transformer.py:294-301, :755-761). */
+int mmpfn_image_tokens(const mmpfn_geometry* g, int n_tok);
+
+/* size in floats of the statistics block mmpfn_stem_tab_fit writes for n_groups groups */
+size_t mmpfn_tab_stats_elems(const mmpfn_geometry* g, int n_groups);
+
+/* Tabular stem statistics — encoders.py:515 (constant-column mask over ALL rows),
+ * :461 (NaN fill means, train rows), :133-162 (two-pass 12-sigma bounds), :53-99 (z-norm mean/std),
+ * :615-619 (used-feature count).  x: [B][S][F] fp32 (NaN allowed); stats: [B][tab_stats_elems].
+ * F is padded to a multiple of features_per_group internally (transformer.py:630-648). */
+int mmpfn_stem_tab_fit(const mmpfn_geometry* g, const float* x, int B, int S, int F, int n_train,
+                       float n_sigma, float* stats, void* stream);
+
+/* Image/text mixer — transformer.py:33-48 (MGM), :60-88 (CAP), :91-128 (MoE).
+ * img: [S][n_tok][img_dim] fp32 -> out: [S][H_img][E] fp32.  workspace: mmpfn_stem_image_ws_bytes. */
+size_t mmpfn_stem_image_ws_bytes(const mmpfn_geometry* g, int S, int n_tok);
+int mmpfn_stem_image(const mmpfn_geometry* g, const mmpfn_weights* w, const float* img, int S, int n_tok,
+                     float* out, void* workspace, size_t workspace_bytes, void* stream);
+
+/* Token assembly — transformer.py:682-788: tabular groups (encoders.py:382-425 after the fitted
+ * transforms), image tokens, + positional embedding on every non-y token, y token last
+ * (encoders.py:428-493, :949-974; rows with NaN label are test rows).
+ *   x       [B][.][F] or NULL: S rows per estimator starting at x, estimators x_bstride elements apart
+ *           (so the train rows and the test rows of one [B][S_full][F] table embed separately)
+ *   stats   [B][tab_stats_elems] or NULL
+ *   img_tok [S][H_img][E] or NULL      (shared by the B estimators, inference.py:272)
+ *   y       [B][.]: S labels per estimator, y_bstride apart (NaN = unlabeled test row)
+ *   y_mean  [B], y_present_mask [B] (bit c set iff class c occurs among the train labels)
+ *   pos_emb [T-1][E]
+ *   state_f32 [B][S][T][E] out; state_bf16 same shape, may be NULL.
+ * nan_flag (int32, device): set to 1 if any produced value is NaN (transformer.py:727-731, :790-796). */
+int mmpfn_stem_tokens(const mmpfn_geometry* g, const mmpfn_weights* w, const float* x, const float* stats,
+                      const float* img_tok, const float* y, const float* y_mean, const uint64_t* y_present_mask,
+                      const float* pos_emb, int B, int S, int F, int H_img, long long x_bstride, long long y_bstride,
+                      float* state_f32, uint16_t* state_bf16, int32_t* nan_flag, void* stream);
+
+/* ---- the 12 layers ------------------------------------------------------------------------- */
+/* Bytes of scratch mmpfn_layers_* need for a [B][S][T][E] state. */
+size_t mmpfn_layers_ws_bytes(const mmpfn_geometry* g, int B, int S, int T, int precision);
+/* Bytes of the K/V context of n_train rows: per layer, head-0 keys and values of the item
+ * attention for every (estimator, token column) — the reference's "first head only" cache
+ * (multi_head_attention.py:328-336, :467-470) with a layer axis in front. */
+size_t mmpfn_kv_bytes(const mmpfn_geometry* g, int B, int n_train, int T, int precision);
+
+/* Train rows: layer.py:272-457 with every row a train row (self-attention over items, all heads,
+ * layer.py:363-372); writes the head-0 K/V context when kv != NULL.  state is updated in place. */
+int mmpfn_layers_train(const mmpfn_geometry* g, const mmpfn_weights* w, float* state_f32, uint16_t* state_bf16,
+                       int B, int S, int T, int precision, void* kv, void* workspace, size_t workspace_bytes,
+                       void* stream);
+/* Test rows: item attention reads the cached head-0 K/V of the n_train train rows for all six
+ * query heads (layer.py:346-358, multi_head_attention.py:436-445). */
+int mmpfn_layers_test(const mmpfn_geometry* g, const mmpfn_weights* w, float* state_f32, uint16_t* state_bf16,
+                      int B, int S, int T, int n_train, int precision, const void* kv, void* workspace,
+                      size_t workspace_bytes, void* stream);
+
+/* ---- decoder + probability tail ------------------------------------------------------------ */
+/* transformer.py:392-396, :850-853: logits[b][s][:] = W2 gelu(W1 state[b][s][T-1] + b1) + b2.
+ * state [B][S][T][E] -> logits [B][S][n_out]; hidden scratch [B*S][nhid] fp32. */
+int mmpfn_decode(const mmpfn_geometry* g, const mmpfn_weights* w, const float* state_f32, int B, int S, int T,
+                 float* hidden_scratch, float* logits, void* stream);
+
+/* classifier.py:544-576: per estimator (slice to n_classes and divide by temperature iff
+ * temperature != 1) -> gather class_perm -> softmax -> mean over estimators (or mean then softmax)
+ * -> optional class-prior balancing -> renormalise.  logits [n_est][S][n_out]; class_perm
+ * [n_est][n_classes] int32; class_prior [n_classes] or NULL; proba [S][n_classes]. */
+int mmpfn_proba_tail(const float* logits, const int32_t* class_perm, const float* class_prior, int n_est, int S,
+                     int n_out, int n_classes, float temperature, int average_before_softmax, float* proba,
+                     void* stream);
+
+/* ---- building blocks exported for unit tests and profiling ---------------------------------- */
+/* y = LayerNorm(x (+ res)) over `width` (192 or 768), eps 1e-5, optional affine (layer.py:40-64). */
+int mmpfn_layernorm(const float* x, const float* res, const float* gamma, const float* beta, int rows, int width,
+                    float* y_f32, uint16_t* y_bf16, void* stream);
+/* out[M][N] = epi(A[M][K] W[N][K]^T + bias); epi: 0 none, 1 exact GELU.  fp32 FFMA kernel. */
+int mmpfn_linear_f32(const float* A, const float* W, const float* bias, int M, int N, int K, int epi, float* out,
+                     void* stream);
+/* Same contract on the tcgen05 path: A, W bf16; out bf16. */
+int mmpfn_linear_bf16(const uint16_t* A, const uint16_t* W, int M, int N, int K, int epi, uint16_t* out,
+                      void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MMPFN_B200_H */

@@ -1,0 +1,733 @@
+// kernels_tc.cu — the tensor-core path (bf16 operands, fp32 accumulation) written directly against
+// sm_100a: TMA (cp.async.bulk.tensor) stages 128B/64B-swizzled tiles in shared memory, a single
+// elected thread issues tcgen05.mma with accumulators in TMEM, epilogue / softmax warps read them
+// back with tcgen05.ld.  Two kernels:
+//
+//   tc_gemm_kernel       out = epi(A W^T), 128 x 192 x 64 tiles.  Serves the QKV / output
+//                        projections (multi_head_attention.py:430, :513-517) and the MLP
+//                        (mlp.py:93-104).  Epilogues: bf16 store, exact GELU, residual + LayerNorm
+//                        (layer.py:437-455), and the item-attention QKV scatter.
+//   tc_item_attn_kernel  flash attention across items (layer.py:341-379), d = 32: S = Q K^T and
+//                        O += P V on tcgen05, online softmax in fp32 by four warps.
+//
+// Every mbarrier wait is bounded (trap after ~2 s) so that a protocol bug cannot hang the GPU.
+#include <cuda.h>
+#include <stdio.h>
+
+#include "common.cuh"
+
+namespace mmpfn {
+namespace {
+
+// ---------------------------------------------------------------------------------------------
+// PTX wrappers
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(ok)
+      : "r"(smem_u32(bar)), "r"(parity)
+      : "memory");
+  return ok != 0;
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  if (mbar_try_wait(bar, parity)) return;
+  const long long t0 = clock64();
+  while (!mbar_try_wait(bar, parity)) {
+    if (clock64() - t0 > 4000000000LL) {   // ~2 s: a protocol bug, not a slow tile
+      printf("mmpfn: mbarrier timeout (block %d,%d thread %d)\n", blockIdx.x, blockIdx.y, threadIdx.x);
+      __trap();
+    }
+  }
+}
+__device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+__device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+      ::"r"(smem_u32(dst)), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ void tma_load_3d(void* dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1, int c2) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+      ::"r"(smem_u32(dst)), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2)
+      : "memory");
+}
+__device__ __forceinline__ void tma_load_4d(void* dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1, int c2,
+                                            int c3) {
+  asm volatile(
+      "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
+      ::"r"(smem_u32(dst)), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
+      : "memory");
+}
+__device__ __forceinline__ void prefetch_tmap(const CUtensorMap* map) {
+  asm volatile("prefetch.tensormap [%0];" ::"l"(map) : "memory");
+}
+
+__device__ __forceinline__ void tmem_alloc(uint32_t* dst_smem, uint32_t ncols) {   // whole warp
+  asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(dst_smem)), "r"(ncols)
+               : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t ncols) {     // whole warp
+  asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+// D[tmem] (+)= A[smem] * B[smem]^T, bf16 x bf16 -> fp32; one thread issues for the CTA
+__device__ __forceinline__ void umma_bf16(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
+                                          uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// arrive on an mbarrier once every tcgen05 op issued so far by this thread has completed
+__device__ __forceinline__ void umma_commit(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
+               : "memory");
+}
+// 32 lanes x 32 consecutive fp32 columns: thread i of the warp gets TMEM lane (base lane + i)
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
+        "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]),
+        "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]),
+        "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+      : "r"(taddr)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+__device__ __forceinline__ void tmem_st32(uint32_t taddr, const uint32_t (&v)[32]) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], "
+      "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, "
+      "%17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31, %32};"
+      ::"r"(taddr), "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7]), "r"(v[8]),
+        "r"(v[9]), "r"(v[10]), "r"(v[11]), "r"(v[12]), "r"(v[13]), "r"(v[14]), "r"(v[15]), "r"(v[16]), "r"(v[17]),
+        "r"(v[18]), "r"(v[19]), "r"(v[20]), "r"(v[21]), "r"(v[22]), "r"(v[23]), "r"(v[24]), "r"(v[25]), "r"(v[26]),
+        "r"(v[27]), "r"(v[28]), "r"(v[29]), "r"(v[30]), "r"(v[31])
+      : "memory");
+}
+__device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+
+__device__ __forceinline__ float fast_exp2(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+
+// UMMA shared-memory operand descriptor, K-major, swizzled (cute::UMMA::SmemDescriptor layout):
+// start address >> 4 in [0,14), LBO (=1, unused for swizzled K-major) in [16,30), SBO >> 4 in [32,46),
+// version 1 in [46,48), layout type in [61,64) (2 = 128B swizzle, 4 = 64B swizzle).
+constexpr uint32_t kSw128 = 2, kSw64 = 4;
+__device__ __forceinline__ uint64_t make_desc(uint32_t saddr, uint32_t sbo_bytes, uint32_t layout) {
+  uint64_t d = 0;
+  d |= (uint64_t)((saddr & 0x3FFFFu) >> 4);
+  d |= (uint64_t)1 << 16;
+  d |= (uint64_t)(sbo_bytes >> 4) << 32;
+  d |= (uint64_t)1 << 46;
+  d |= (uint64_t)layout << 61;
+  return d;
+}
+// instruction descriptor (cute::UMMA::InstrDescriptor): fp32 accumulate, bf16 A/B, both K-major
+__host__ __device__ constexpr uint32_t make_idesc(int M, int N) {
+  return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+
+// ---------------------------------------------------------------------------------------------
+// GEMM
+// ---------------------------------------------------------------------------------------------
+constexpr int G_BM = 128, G_BN = 192, G_BK = 64, G_STAGES = 2;
+constexpr int G_A_BYTES = G_BM * G_BK * 2;           // 16 KB
+constexpr int G_B_BYTES = G_BN * G_BK * 2;           // 24 KB
+constexpr int G_STAGE_BYTES = G_A_BYTES + G_B_BYTES;
+constexpr int G_SMEM = G_STAGES * G_STAGE_BYTES + 1024 /*align*/ + 256 /*barriers*/;
+constexpr int G_TMEM_COLS = 256;
+constexpr int G_THREADS = 192;
+
+struct GemmArgs {
+  int M, N, K;
+  int items, B, S, T, tiles_s;
+  uint16_t* out_bf16;
+  float* resid;
+  uint16_t* ln_bf16;
+  uint16_t *q_out, *k_out, *vt_out, *k0_out, *vt0_out;
+  int S_pad;
+};
+
+template <int EPI>
+__global__ void __launch_bounds__(G_THREADS) tc_gemm_kernel(const __grid_constant__ CUtensorMap map_a,
+                                                            const __grid_constant__ CUtensorMap map_w,
+                                                            const GemmArgs p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+  uint64_t* full = (uint64_t*)(smem + G_STAGES * G_STAGE_BYTES);
+  uint64_t* empty = full + G_STAGES;
+  uint64_t* acc_full = empty + G_STAGES;
+  uint32_t* tmem_slot = (uint32_t*)(acc_full + 1);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int KB = p.K / G_BK;
+  const int n0 = blockIdx.y * G_BN;
+
+  // tile coordinates
+  int m0 = 0, tb = 0, tt = 0, s0 = 0;
+  if (p.items) {
+    const int mt = blockIdx.x;
+    const int per_b = p.T * p.tiles_s;
+    tb = mt / per_b;
+    const int r = mt % per_b;
+    tt = r / p.tiles_s;
+    s0 = (r % p.tiles_s) * G_BM;
+  } else {
+    m0 = blockIdx.x * G_BM;
+  }
+
+  if (threadIdx.x == 0) {
+    prefetch_tmap(&map_a);
+    prefetch_tmap(&map_w);
+    for (int s = 0; s < G_STAGES; ++s) {
+      mbar_init(&full[s], 1);
+      mbar_init(&empty[s], 1);
+    }
+    mbar_init(acc_full, 1);
+    fence_barrier_init();
+  }
+  if (warp == 1) tmem_alloc(tmem_slot, G_TMEM_COLS);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = *tmem_slot;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      for (int kb = 0; kb < KB; ++kb) {
+        const int s = kb % G_STAGES;
+        mbar_wait(&empty[s], ((kb / G_STAGES) & 1) ^ 1);
+        uint8_t* a_dst = smem + s * G_STAGE_BYTES;
+        uint8_t* b_dst = a_dst + G_A_BYTES;
+        mbar_expect_tx(&full[s], G_STAGE_BYTES);
+        if (p.items) tma_load_4d(a_dst, &map_a, &full[s], kb * G_BK, tt, s0, tb);
+        else tma_load_2d(a_dst, &map_a, &full[s], kb * G_BK, m0);
+        tma_load_2d(b_dst, &map_w, &full[s], kb * G_BK, n0);
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      constexpr uint32_t idesc = make_idesc(G_BM, G_BN);
+      for (int kb = 0; kb < KB; ++kb) {
+        const int s = kb % G_STAGES;
+        mbar_wait(&full[s], (kb / G_STAGES) & 1);
+        tc_fence_after();
+        const uint32_t a_addr = smem_u32(smem + s * G_STAGE_BYTES);
+        const uint64_t adesc = make_desc(a_addr, 1024, kSw128);
+        const uint64_t bdesc = make_desc(a_addr + G_A_BYTES, 1024, kSw128);
+#pragma unroll
+        for (int k = 0; k < G_BK / 16; ++k)
+          umma_bf16(tmem, adesc + (uint64_t)(k * 2), bdesc + (uint64_t)(k * 2), idesc, (kb | k) != 0);
+        umma_commit(&empty[s]);
+      }
+      umma_commit(acc_full);
+    }
+  } else {
+    // ---- epilogue: 4 warps, warp w owns TMEM lanes [32*(w%4), +32) = tile rows ----
+    const int quarter = warp & 3;
+    const int r = quarter * 32 + lane;
+    const uint32_t trow = tmem + ((uint32_t)(quarter * 32) << 16);
+    mbar_wait(acc_full, 0);
+    tc_fence_after();
+    uint32_t v[32];
+    if (EPI == TC_EPI_BF16 || EPI == TC_EPI_GELU_BF16) {
+      const long long m = (long long)m0 + r;
+      const bool ok = m < p.M;
+      uint16_t* dst = p.out_bf16 + m * p.N + n0;
+#pragma unroll 1
+      for (int c = 0; c < G_BN / 32; ++c) {
+        tmem_ld32(trow + c * 32, v);
+        tmem_ld_wait();
+        if (ok) {
+          uint32_t pk[16];
+#pragma unroll
+          for (int i = 0; i < 16; ++i) {
+            float a = __uint_as_float(v[2 * i]), b = __uint_as_float(v[2 * i + 1]);
+            if (EPI == TC_EPI_GELU_BF16) { a = gelu_exact(a); b = gelu_exact(b); }
+            pk[i] = pack_bf16x2(a, b);
+          }
+          uint4* d4 = reinterpret_cast<uint4*>(dst + c * 32);
+#pragma unroll
+          for (int i = 0; i < 4; ++i) d4[i] = make_uint4(pk[4 * i], pk[4 * i + 1], pk[4 * i + 2], pk[4 * i + 3]);
+        }
+      }
+    } else if (EPI == TC_EPI_RESID_LN) {
+      // state = LN(state + acc): pass 1 adds the residual, keeps v in TMEM and accumulates the
+      // statistics; pass 2 normalises and writes the fp32 state and its bf16 shadow.
+      const long long m = (long long)m0 + r;
+      const bool ok = m < p.M;
+      float* res = p.resid + m * kE;
+      float sum = 0.f, sq = 0.f;
+#pragma unroll 1
+      for (int c = 0; c < kE / 32; ++c) {
+        tmem_ld32(trow + c * 32, v);
+        tmem_ld_wait();
+        if (ok) {
+          const float4* r4 = reinterpret_cast<const float4*>(res + c * 32);
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            const float4 rr = r4[i];
+            const float a0 = __uint_as_float(v[4 * i]) + rr.x, a1 = __uint_as_float(v[4 * i + 1]) + rr.y,
+                        a2 = __uint_as_float(v[4 * i + 2]) + rr.z, a3 = __uint_as_float(v[4 * i + 3]) + rr.w;
+            sum += (a0 + a1) + (a2 + a3);
+            sq = fmaf(a0, a0, sq); sq = fmaf(a1, a1, sq); sq = fmaf(a2, a2, sq); sq = fmaf(a3, a3, sq);
+            v[4 * i] = __float_as_uint(a0); v[4 * i + 1] = __float_as_uint(a1);
+            v[4 * i + 2] = __float_as_uint(a2); v[4 * i + 3] = __float_as_uint(a3);
+          }
+        }
+        tmem_st32(trow + c * 32, v);
+      }
+      tmem_st_wait();
+      const float mean = sum * (1.0f / kE);
+      const float var = fmaxf(sq * (1.0f / kE) - mean * mean, 0.f);
+      const float rstd = rsqrtf(var + kLnEps);
+      uint16_t* lnb = p.ln_bf16 + m * kE;
+#pragma unroll 1
+      for (int c = 0; c < kE / 32; ++c) {
+        tmem_ld32(trow + c * 32, v);
+        tmem_ld_wait();
+        if (ok) {
+          float y[32];
+#pragma unroll
+          for (int i = 0; i < 32; ++i) y[i] = (__uint_as_float(v[i]) - mean) * rstd;
+          float4* o4 = reinterpret_cast<float4*>(res + c * 32);
+#pragma unroll
+          for (int i = 0; i < 8; ++i) o4[i] = make_float4(y[4 * i], y[4 * i + 1], y[4 * i + 2], y[4 * i + 3]);
+          uint4* b4 = reinterpret_cast<uint4*>(lnb + c * 32);
+#pragma unroll
+          for (int i = 0; i < 4; ++i)
+            b4[i] = make_uint4(pack_bf16x2(y[8 * i], y[8 * i + 1]), pack_bf16x2(y[8 * i + 2], y[8 * i + 3]),
+                               pack_bf16x2(y[8 * i + 4], y[8 * i + 5]), pack_bf16x2(y[8 * i + 6], y[8 * i + 7]));
+        }
+      }
+    } else {  // TC_EPI_QKV_ITEMS: n-tile j in {q,k,v}; 32-column chunk c = head
+      const int s = s0 + r;
+      const bool ok = s < p.S;
+      const int j = blockIdx.y;
+      const long long bt = (long long)tb * p.T + tt;
+#pragma unroll 1
+      for (int h = 0; h < kH; ++h) {
+        tmem_ld32(trow + h * 32, v);
+        tmem_ld_wait();
+        if (!ok) continue;
+        const long long plane = bt * kH + h;
+        if (j < 2) {
+          uint32_t pk[16];
+#pragma unroll
+          for (int i = 0; i < 16; ++i) pk[i] = pack_bf16x2(__uint_as_float(v[2 * i]), __uint_as_float(v[2 * i + 1]));
+          uint16_t* dst = (j == 0 ? p.q_out : p.k_out) + (plane * p.S_pad + s) * kD;
+          uint4* d4 = reinterpret_cast<uint4*>(dst);
+#pragma unroll
+          for (int i = 0; i < 4; ++i) d4[i] = make_uint4(pk[4 * i], pk[4 * i + 1], pk[4 * i + 2], pk[4 * i + 3]);
+          if (j == 1 && h == 0 && p.k0_out) {
+            uint4* c4 = reinterpret_cast<uint4*>(p.k0_out + (bt * p.S_pad + s) * kD);
+#pragma unroll
+            for (int i = 0; i < 4; ++i) c4[i] = make_uint4(pk[4 * i], pk[4 * i + 1], pk[4 * i + 2], pk[4 * i + 3]);
+          }
+        } else {
+          // V is stored transposed ([d][s]) so that P V is a K-major x K-major MMA; consecutive
+          // lanes hold consecutive s -> 64 B coalesced per d
+          uint16_t* dst = p.vt_out + plane * kD * p.S_pad + s;
+          uint16_t* dst0 = (h == 0 && p.vt0_out) ? p.vt0_out + bt * kD * p.S_pad + s : nullptr;
+#pragma unroll
+          for (int d = 0; d < kD; ++d) {
+            __nv_bfloat16 bv = __float2bfloat16_rn(__uint_as_float(v[d]));
+            const uint16_t bits = *reinterpret_cast<uint16_t*>(&bv);
+            dst[(long long)d * p.S_pad] = bits;
+            if (dst0) dst0[(long long)d * p.S_pad] = bits;
+          }
+        }
+      }
+    }
+    tc_fence_before();
+  }
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem, G_TMEM_COLS);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// host: tensor maps
+// ---------------------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+EncodeTiledFn get_encode() {
+  static EncodeTiledFn fn = nullptr;
+  if (!fn) {
+    void* ptr = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &q) != cudaSuccess ||
+        q != cudaDriverEntryPointSuccess) {
+      cudaGetLastError();
+      return nullptr;
+    }
+    fn = (EncodeTiledFn)ptr;
+  }
+  return fn;
+}
+
+// bf16 tensor, dims innermost first; strides in bytes for dims 1..rank-1
+int encode_map(CUtensorMap* m, const void* base, int rank, const cuuint64_t* dims, const cuuint64_t* strides,
+               const cuuint32_t* box, CUtensorMapSwizzle sw) {
+  EncodeTiledFn fn = get_encode();
+  if (!fn) { set_error("cuTensorMapEncodeTiled not available"); return MMPFN_ECUDA; }
+  cuuint32_t ones[5] = {1, 1, 1, 1, 1};
+  CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, (cuuint32_t)rank, const_cast<void*>(base), dims, strides, box,
+                  ones, CU_TENSOR_MAP_INTERLEAVE_NONE, sw, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    set_error("cuTensorMapEncodeTiled failed (%d) rank %d dims %llu,%llu box %u,%u", (int)r, rank,
+              (unsigned long long)dims[0], (unsigned long long)dims[1], box[0], box[1]);
+    return MMPFN_ECUDA;
+  }
+  return MMPFN_OK;
+}
+
+template <int EPI>
+int launch_gemm_t(const CUtensorMap& ma, const CUtensorMap& mw, const GemmArgs& a, dim3 grid, cudaStream_t st) {
+  static bool configured = false;
+  if (!configured) {
+    cudaFuncSetAttribute(tc_gemm_kernel<EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, G_SMEM);
+    configured = true;
+  }
+  tc_gemm_kernel<EPI><<<grid, G_THREADS, G_SMEM, st>>>(ma, mw, a);
+  return count_launch();
+}
+
+}  // namespace
+
+int launch_tc_gemm(const TcGemm& p, cudaStream_t st) {
+  if (p.K % G_BK != 0 || p.N % G_BN != 0) {
+    set_error("tc_gemm: N=%d must be a multiple of %d and K=%d of %d", p.N, G_BN, p.K, G_BK);
+    return MMPFN_EUNSUPPORTED;
+  }
+  if (p.epi == TC_EPI_RESID_LN && p.N != kE) { set_error("tc_gemm: LN epilogue needs N=%d", kE); return MMPFN_EINVAL; }
+  GemmArgs a{};
+  a.M = p.M; a.N = p.N; a.K = p.K; a.items = p.items; a.B = p.B; a.S = p.S; a.T = p.T;
+  a.out_bf16 = p.out_bf16; a.resid = p.resid_f32; a.ln_bf16 = p.ln_bf16;
+  a.q_out = p.q_out; a.k_out = p.k_out; a.vt_out = p.vt_out; a.k0_out = p.k0_out; a.vt0_out = p.vt0_out;
+  a.S_pad = p.S_pad;
+  CUtensorMap ma, mw;
+  dim3 grid;
+  if (p.items) {
+    if (p.epi != TC_EPI_QKV_ITEMS) { set_error("tc_gemm: item tiles need the QKV epilogue"); return MMPFN_EINVAL; }
+    a.tiles_s = (p.S + G_BM - 1) / G_BM;
+    const cuuint64_t dims[4] = {(cuuint64_t)p.K, (cuuint64_t)p.T, (cuuint64_t)p.S, (cuuint64_t)p.B};
+    const cuuint64_t strides[3] = {(cuuint64_t)p.K * 2, (cuuint64_t)p.T * p.K * 2, (cuuint64_t)p.S * p.T * p.K * 2};
+    const cuuint32_t box[4] = {G_BK, 1, G_BM, 1};
+    MMPFN_TRY(encode_map(&ma, p.A, 4, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_128B));
+    grid = dim3((unsigned)(p.B * p.T * a.tiles_s), p.N / G_BN);
+  } else {
+    if (p.M <= 0) return MMPFN_OK;
+    const cuuint64_t dims[2] = {(cuuint64_t)p.K, (cuuint64_t)p.M};
+    const cuuint64_t strides[1] = {(cuuint64_t)p.K * 2};
+    const cuuint32_t box[2] = {G_BK, G_BM};
+    MMPFN_TRY(encode_map(&ma, p.A, 2, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_128B));
+    grid = dim3((unsigned)((p.M + G_BM - 1) / G_BM), p.N / G_BN);
+  }
+  {
+    const cuuint64_t dims[2] = {(cuuint64_t)p.K, (cuuint64_t)p.N};
+    const cuuint64_t strides[1] = {(cuuint64_t)p.K * 2};
+    const cuuint32_t box[2] = {G_BK, G_BN};
+    MMPFN_TRY(encode_map(&mw, p.W, 2, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_128B));
+  }
+  switch (p.epi) {
+    case TC_EPI_BF16: return launch_gemm_t<TC_EPI_BF16>(ma, mw, a, grid, st);
+    case TC_EPI_GELU_BF16: return launch_gemm_t<TC_EPI_GELU_BF16>(ma, mw, a, grid, st);
+    case TC_EPI_RESID_LN: return launch_gemm_t<TC_EPI_RESID_LN>(ma, mw, a, grid, st);
+    case TC_EPI_QKV_ITEMS: return launch_gemm_t<TC_EPI_QKV_ITEMS>(ma, mw, a, grid, st);
+  }
+  set_error("tc_gemm: bad epilogue %d", p.epi);
+  return MMPFN_EINVAL;
+}
+
+// ---------------------------------------------------------------------------------------------
+// Item attention
+// ---------------------------------------------------------------------------------------------
+namespace {
+constexpr int A_BQ = 128, A_BK = 128;
+constexpr int A_Q_BYTES = A_BQ * kD * 2;          // 8 KB  (64B rows, 64B swizzle)
+constexpr int A_K_BYTES = A_BK * kD * 2;          // 8 KB
+constexpr int A_VT_BYTES = kD * A_BK * 2;         // 8 KB = 2 k-blocks x [32 rows][128 B], 128B swizzle
+constexpr int A_P_BYTES = A_BQ * A_BK * 2;        // 32 KB = 2 k-blocks x [128 rows][128 B], 128B swizzle
+constexpr int A_KV_STAGES = 2;
+constexpr int A_OFF_K = A_Q_BYTES;
+constexpr int A_OFF_VT = A_OFF_K + A_KV_STAGES * A_K_BYTES;
+constexpr int A_OFF_P = A_OFF_VT + A_KV_STAGES * A_VT_BYTES;
+constexpr int A_OFF_BAR = A_OFF_P + A_P_BYTES;
+constexpr int A_SMEM = A_OFF_BAR + 256 + 1024;
+constexpr int A_TMEM_COLS = 256;                  // S: [0,128)  O: [128,160)
+constexpr int A_THREADS = 192;
+
+struct AttnArgs {
+  uint16_t* out;
+  int T, n_q, n_kv, shared_kv;
+};
+
+__global__ void __launch_bounds__(A_THREADS) tc_item_attn_kernel(const __grid_constant__ CUtensorMap map_q,
+                                                                 const __grid_constant__ CUtensorMap map_k,
+                                                                 const __grid_constant__ CUtensorMap map_vt,
+                                                                 const AttnArgs p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+  uint64_t* bars = (uint64_t*)(smem + A_OFF_BAR);
+  uint64_t* q_full = bars;
+  uint64_t* kv_full = bars + 1;        // [2]
+  uint64_t* kv_empty = bars + 3;       // [2]
+  uint64_t* s_full = bars + 5;
+  uint64_t* p_full = bars + 6;
+  uint64_t* pv_done = bars + 7;
+  uint32_t* tmem_slot = (uint32_t*)(bars + 8);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int plane = blockIdx.x;                 // (b*T + t)*kH + h
+  const int q0 = blockIdx.y * A_BQ;
+  const int h = plane % kH;
+  const int bt = plane / kH;
+  const int kv_plane = p.shared_kv ? bt : plane;
+  const int nkt = (p.n_kv + A_BK - 1) / A_BK;
+
+  if (threadIdx.x == 0) {
+    prefetch_tmap(&map_q);
+    prefetch_tmap(&map_k);
+    prefetch_tmap(&map_vt);
+    mbar_init(q_full, 1);
+    for (int s = 0; s < A_KV_STAGES; ++s) {
+      mbar_init(&kv_full[s], 1);
+      mbar_init(&kv_empty[s], 1);
+    }
+    mbar_init(s_full, 1);
+    mbar_init(p_full, 128);
+    mbar_init(pv_done, 1);
+    fence_barrier_init();
+  }
+  if (warp == 1) tmem_alloc(tmem_slot, A_TMEM_COLS);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem = *tmem_slot;
+  const uint32_t tmem_s = tmem, tmem_o = tmem + 128;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      mbar_expect_tx(q_full, A_Q_BYTES);
+      tma_load_3d(smem, &map_q, q_full, 0, q0, plane);
+      for (int j = 0; j < nkt; ++j) {
+        const int s = j % A_KV_STAGES;
+        mbar_wait(&kv_empty[s], ((j / A_KV_STAGES) & 1) ^ 1);
+        mbar_expect_tx(&kv_full[s], A_K_BYTES + A_VT_BYTES);
+        tma_load_3d(smem + A_OFF_K + s * A_K_BYTES, &map_k, &kv_full[s], 0, j * A_BK, kv_plane);
+        tma_load_3d(smem + A_OFF_VT + s * A_VT_BYTES, &map_vt, &kv_full[s], j * A_BK, 0, kv_plane);
+        tma_load_3d(smem + A_OFF_VT + s * A_VT_BYTES + A_VT_BYTES / 2, &map_vt, &kv_full[s], j * A_BK + 64, 0,
+                    kv_plane);
+      }
+    }
+  } else if (warp == 1) {
+    if (lane == 0) {
+      constexpr uint32_t idesc_s = make_idesc(A_BQ, A_BK);
+      constexpr uint32_t idesc_o = make_idesc(A_BQ, kD);
+      const uint32_t sbase = smem_u32(smem);
+      const uint64_t qdesc = make_desc(sbase, 512, kSw64);
+      auto issue_s = [&](int j) {
+        const int s = j % A_KV_STAGES;
+        mbar_wait(&kv_full[s], (j / A_KV_STAGES) & 1);
+        tc_fence_after();
+        const uint64_t kdesc = make_desc(sbase + A_OFF_K + s * A_K_BYTES, 512, kSw64);
+#pragma unroll
+        for (int k = 0; k < kD / 16; ++k)
+          umma_bf16(tmem_s, qdesc + (uint64_t)(k * 2), kdesc + (uint64_t)(k * 2), idesc_s, k != 0);
+        umma_commit(s_full);
+      };
+      mbar_wait(q_full, 0);
+      issue_s(0);
+      for (int j = 0; j < nkt; ++j) {
+        const int s = j % A_KV_STAGES;
+        mbar_wait(p_full, j & 1);              // P(j) is in shared memory, S(j) has been read out of TMEM
+        tc_fence_after();
+        if (j + 1 < nkt) issue_s(j + 1);
+#pragma unroll
+        for (int k = 0; k < A_BK / 16; ++k) {
+          const uint64_t pdesc = make_desc(sbase + A_OFF_P + (k / 4) * (A_P_BYTES / 2) + (k % 4) * 32, 1024, kSw128);
+          const uint64_t vdesc =
+              make_desc(sbase + A_OFF_VT + s * A_VT_BYTES + (k / 4) * (A_VT_BYTES / 2) + (k % 4) * 32, 1024, kSw128);
+          umma_bf16(tmem_o, pdesc, vdesc, idesc_o, (j | k) != 0);
+        }
+        umma_commit(&kv_empty[s]);
+        umma_commit(pv_done);
+      }
+    }
+  } else {
+    // ---- softmax warps: thread = one query row ----
+    const int quarter = warp & 3;
+    const int r = quarter * 32 + lane;
+    const uint32_t lane_off = (uint32_t)(quarter * 32) << 16;
+    const float c = 0.17677669529663687f * 1.4426950408889634f;   // log2(e)/sqrt(d)
+    uint8_t* prow = smem + A_OFF_P + r * 128;
+    const int rsw = r & 7;
+    float m_run = -INFINITY, l_run = 0.f;
+    uint32_t v[32];
+    for (int j = 0; j < nkt; ++j) {
+      mbar_wait(s_full, j & 1);
+      tc_fence_after();
+      const int valid = p.n_kv - j * A_BK;       // keys of this tile that exist
+      // pass 1: row maximum
+      float mx = -INFINITY;
+#pragma unroll 1
+      for (int cc = 0; cc < 4; ++cc) {
+        tmem_ld32(tmem_s + lane_off + cc * 32, v);
+        tmem_ld_wait();
+        if (valid >= A_BK) {
+#pragma unroll
+          for (int i = 0; i < 32; ++i) mx = fmaxf(mx, __uint_as_float(v[i]));
+        } else {
+#pragma unroll
+          for (int i = 0; i < 32; ++i)
+            if (cc * 32 + i < valid) mx = fmaxf(mx, __uint_as_float(v[i]));
+        }
+      }
+      const float m_new = fmaxf(m_run, mx);
+      const float alpha = fast_exp2((m_run - m_new) * c);
+      const float mc = m_new * c;
+      // P(j-1) must have been consumed by its MMA before P is overwritten / O is rescaled
+      if (j > 0) {
+        mbar_wait(pv_done, (j - 1) & 1);
+        tc_fence_after();
+      }
+      // pass 2: p = exp2(s*c - m*c), bf16 into the 128B-swizzled A tile of the PV MMA
+      float lsum = 0.f;
+#pragma unroll 1
+      for (int cc = 0; cc < 4; ++cc) {
+        tmem_ld32(tmem_s + lane_off + cc * 32, v);
+        tmem_ld_wait();
+        uint32_t pk[16];
+#pragma unroll
+        for (int i = 0; i < 16; ++i) {
+          float a = fast_exp2(fmaf(__uint_as_float(v[2 * i]), c, -mc));
+          float b = fast_exp2(fmaf(__uint_as_float(v[2 * i + 1]), c, -mc));
+          if (valid < A_BK) {
+            if (cc * 32 + 2 * i >= valid) a = 0.f;
+            if (cc * 32 + 2 * i + 1 >= valid) b = 0.f;
+          }
+          lsum += a + b;
+          pk[i] = pack_bf16x2(a, b);
+        }
+        // 32 keys = 4 chunks of 16 B inside k-block (cc / 2); chunk index XOR (row & 7)
+        uint8_t* kb = prow + (cc >> 1) * (A_P_BYTES / 2);
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          const int chunk = (cc & 1) * 4 + q;
+          *reinterpret_cast<uint4*>(kb + ((chunk ^ rsw) << 4)) =
+              make_uint4(pk[4 * q], pk[4 * q + 1], pk[4 * q + 2], pk[4 * q + 3]);
+        }
+      }
+      l_run = l_run * alpha + lsum;
+      m_run = m_new;
+      // rescale the running output when some row of this warp moved its maximum
+      if (j > 0 && __any_sync(0xffffffffu, alpha != 1.0f)) {
+        tmem_ld32(tmem_o + lane_off, v);
+        tmem_ld_wait();
+#pragma unroll
+        for (int i = 0; i < 32; ++i) v[i] = __float_as_uint(__uint_as_float(v[i]) * alpha);
+        tmem_st32(tmem_o + lane_off, v);
+        tmem_st_wait();
+      }
+      fence_proxy_async();
+      tc_fence_before();
+      mbar_arrive(p_full);
+    }
+    mbar_wait(pv_done, (nkt - 1) & 1);
+    tc_fence_after();
+    tmem_ld32(tmem_o + lane_off, v);
+    tmem_ld_wait();
+    const int qi = q0 + r;
+    if (qi < p.n_q) {
+      const float inv = 1.0f / l_run;
+      const int b = bt / p.T, t = bt % p.T;
+      uint16_t* dst = p.out + (((long long)b * p.n_q + qi) * p.T + t) * kE + h * kD;
+      uint4* d4 = reinterpret_cast<uint4*>(dst);
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+        d4[i] = make_uint4(pack_bf16x2(__uint_as_float(v[8 * i]) * inv, __uint_as_float(v[8 * i + 1]) * inv),
+                           pack_bf16x2(__uint_as_float(v[8 * i + 2]) * inv, __uint_as_float(v[8 * i + 3]) * inv),
+                           pack_bf16x2(__uint_as_float(v[8 * i + 4]) * inv, __uint_as_float(v[8 * i + 5]) * inv),
+                           pack_bf16x2(__uint_as_float(v[8 * i + 6]) * inv, __uint_as_float(v[8 * i + 7]) * inv));
+    }
+    tc_fence_before();
+  }
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem, A_TMEM_COLS);
+  }
+}
+}  // namespace
+
+int launch_tc_item_attn(const TcItemAttn& p, cudaStream_t st) {
+  if (p.n_q <= 0 || p.B <= 0) return MMPFN_OK;
+  if (p.n_kv <= 0) { set_error("item attention: empty key set"); return MMPFN_EINVAL; }
+  const long long planes_q = (long long)p.B * p.T * kH;
+  const long long planes_kv = p.shared_kv ? (long long)p.B * p.T : planes_q;
+  const int q_tiles = (p.n_q + A_BQ - 1) / A_BQ;
+  if (q_tiles > 65535) { set_error("item attention: %d query tiles exceed grid.y", q_tiles); return MMPFN_EUNSUPPORTED; }
+  CUtensorMap mq, mk, mvt;
+  {
+    const cuuint64_t dims[3] = {(cuuint64_t)kD, (cuuint64_t)p.n_q, (cuuint64_t)planes_q};
+    const cuuint64_t strides[2] = {(cuuint64_t)kD * 2, (cuuint64_t)p.Sq_pad * kD * 2};
+    const cuuint32_t box[3] = {kD, A_BQ, 1};
+    MMPFN_TRY(encode_map(&mq, p.q, 3, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_64B));
+  }
+  {
+    const cuuint64_t dims[3] = {(cuuint64_t)kD, (cuuint64_t)p.n_kv, (cuuint64_t)planes_kv};
+    const cuuint64_t strides[2] = {(cuuint64_t)kD * 2, (cuuint64_t)p.Skv_pad * kD * 2};
+    const cuuint32_t box[3] = {kD, A_BK, 1};
+    MMPFN_TRY(encode_map(&mk, p.k, 3, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_64B));
+  }
+  {
+    const cuuint64_t dims[3] = {(cuuint64_t)p.n_kv, (cuuint64_t)kD, (cuuint64_t)planes_kv};
+    const cuuint64_t strides[2] = {(cuuint64_t)p.Skv_pad * 2, (cuuint64_t)p.Skv_pad * kD * 2};
+    const cuuint32_t box[3] = {64, kD, 1};
+    MMPFN_TRY(encode_map(&mvt, p.vt, 3, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_128B));
+  }
+  static bool configured = false;
+  if (!configured) {
+    cudaFuncSetAttribute(tc_item_attn_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, A_SMEM);
+    configured = true;
+  }
+  AttnArgs a{p.out, p.T, p.n_q, p.n_kv, p.shared_kv};
+  tc_item_attn_kernel<<<dim3((unsigned)planes_q, q_tiles), A_THREADS, A_SMEM, st>>>(mq, mk, mvt, a);
+  return count_launch();
+}
+
+}  // namespace mmpfn

