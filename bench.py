@@ -1,0 +1,422 @@
+#!/usr/bin/env python
+"""bench.py — test rows/s of MMPFN ``predict_proba`` on B200 (BASELINE.json metric).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+
+Workload at N=1 (BASELINE.json configs[1]): PAD-UFES-20 shape — 2000 train / 300 test rows,
+21 tabular features + one 768-d image embedding per row, 8 estimators, bf16, random-init
+TabPFN-v2 weights (12 layers, emsize 192) with MGM(8)+CAP(8) image stem.  One *step* = one
+reference-equivalent ``predict_proba`` pass: the train context is rebuilt inside the call exactly
+like the reference does (inference.py:302-348), then the 300 test rows are classified.
+
+* ``value``  — rows/s with every input already resident in HBM (device-timed, CUDA events).
+* ``e2e``    — rows/s through ``MMPFNClassifier.predict_proba`` with HOST buffers: per-estimator
+  host preprocessing, H2D of the test table + test embeddings, D2H of the probabilities.
+* ``roofline`` — the dominant kernel (item-axis attention, tcgen05) timed alone at the workload's
+  shape against the measured bf16 tensor peak (MEASURED_PEAKS.json).
+* ``cpu_baseline`` — the oracle port (oracle/forward_ref.py, fp32 torch on all host cores) on a
+  bounded sample of the same workload, scaled by the algorithmic FLOP ratio.
+
+With N>1 (torchrun, one rank per GPU) every rank classifies its own 300-row test chunk
+(weak scaling); the train context is built once per estimator on its owner rank and the K/V
+context is all-gathered over NCCL (multimodalpfn_b200/dist.py).
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+E, NH, DK, HID, L = 192, 6, 32, 768, 12
+N_EST = 8
+WORKLOAD = "pad_ufes"
+
+
+# --------------------------------------------------------------------------------------------
+# algorithmic FLOP model, 2 FLOP per MAC
+# --------------------------------------------------------------------------------------------
+def flops_estimator(n_tr, n_te, T, layers=L):
+    S = n_tr + n_te
+    feat = S * (8 * T * E * E + 4 * T * T * E)
+    item = 8 * n_tr * T * E * E + 4 * T * n_tr * n_tr * E + 4 * n_te * T * E * E + 4 * T * n_te * n_tr * E
+    mlp = 16 * S * T * E * E
+    return layers * (feat + item + mlp)
+
+
+def flops_item_attention(n_q, n_kv, T, B):
+    return 4.0 * B * T * NH * n_q * n_kv * DK
+
+
+def load_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        with open(p) as f:
+            d = json.load(f)
+        return dict(hbm=d["hbm_gbs"], burst=d["bf16_tflops"], sustained=d["bf16_tflops_sustained"], src="measured")
+    return dict(hbm=6650.0, burst=1590.0, sustained=1400.0, src="fallback")
+
+
+class ClockSampler:
+    """nvidia-smi clocks during the timed region (B200_PROFILING.md)."""
+
+    def __init__(self, index=0):
+        self.index = index
+        self.rows = []
+        self._stop = threading.Event()
+        self._t = None
+
+    def _run(self):
+        q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+        while not self._stop.is_set():
+            try:
+                out = subprocess.run(["nvidia-smi", f"--id={self.index}", f"--query-gpu={q}",
+                                      "--format=csv,noheader,nounits"], capture_output=True, text=True, timeout=5)
+                if out.returncode == 0 and out.stdout.strip():
+                    self.rows.append([c.strip() for c in out.stdout.strip().split(",")])
+            except Exception:
+                pass
+            self._stop.wait(0.1)
+
+    def __enter__(self):
+        self._t = threading.Thread(target=self._run, daemon=True)
+        self._t.start()
+        return self
+
+    def __exit__(self, *a):
+        self._stop.set()
+        self._t.join(timeout=6)
+
+    def summary(self):
+        if not self.rows:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["unavailable"]}
+        sm = sorted(float(r[0]) for r in self.rows if r[0].replace(".", "").isdigit())
+        mx = [float(r[1]) for r in self.rows if r[1].replace(".", "").isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = sorted({names[i] for r in self.rows for i in range(4) if len(r) > 2 + i and r[2 + i] == "Active"})
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": reasons, "samples": len(self.rows)}
+
+
+# --------------------------------------------------------------------------------------------
+# CPU arm: the oracle port on a bounded sample
+# --------------------------------------------------------------------------------------------
+def cpu_sample(n_layers_sample: int, which: str = "quantile_svd"):
+    """Times the oracle on ONE estimator of the workload truncated to ``n_layers_sample`` of the 12
+    (identical-cost) layers, all host threads; returns (seconds, flops of the sample, T)."""
+    import torch
+    from multimodalpfn_b200.preprocessing import make_members
+    from multimodalpfn_b200.synth import Geometry, make_dataset, make_state_dict
+    from oracle import forward_ref as R
+
+    torch.set_num_threads(os.cpu_count() or 1)
+    d = make_dataset(WORKLOAD, 0)
+    geom = Geometry(mgm_heads=8, cap_heads=8, nlayers=n_layers_sample)
+    sd_full = make_state_dict(Geometry(mgm_heads=8, cap_heads=8), seed=1)
+    tsd = R.as_torch_state_dict(sd_full)
+    members = make_members(N_EST, d["X_train"].shape[1], d["n_classes"], np.random.default_rng(0))
+    m = [mm for mm in members if mm.recipe == which][0]
+    Xtr, ytr = m.fit_transform(d["X_train"], d["y_train"])
+    Xte = m.transform(d["X_test"])
+    X = torch.as_tensor(np.concatenate([Xtr, Xte]))
+    img = torch.as_tensor(np.concatenate([d["img_train"], d["img_test"]]))
+    y = torch.as_tensor(ytr)
+    T = (X.shape[1] + 1) // 2 + 8 + 1
+    t0 = time.perf_counter()
+    with torch.inference_mode():
+        R.forward_joint(X, img, y, tsd, geom, seed=0)
+    dt = time.perf_counter() - t0
+    n_tr, n_te = len(ytr), Xte.shape[0]
+    return dt, flops_estimator(n_tr, n_te, T, layers=n_layers_sample), T
+
+
+def full_flops():
+    from multimodalpfn_b200.synth import DATASETS
+    n_tr, n_te = DATASETS[WORKLOAD][:2]
+    return (N_EST // 2) * (flops_estimator(n_tr, n_te, 27) + flops_estimator(n_tr, n_te, 20)), n_tr, n_te
+
+
+def run_reference(args):
+    """--impl reference: the CPU implementation of the path (the oracle port; the reference itself is
+    Python and absent on the GPU box) on all host cores.  Each step is a bounded sample — one
+    estimator, `layers` of its 12 layers — scaled to the full 8-estimator workload by the
+    algorithmic FLOP ratio."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    total, n_tr, n_te = full_flops()
+    # size the sample so that steps+warmup finish in a few minutes: probe one layer first
+    t1, f1, _ = cpu_sample(1)
+    budget = 150.0 / max(args.steps + args.warmup, 1)
+    layers = int(max(1, min(L, budget // max(t1, 1e-3))))
+    for _ in range(args.warmup):
+        cpu_sample(layers)
+    times = []
+    for _ in range(args.steps):
+        dt, fl, T = cpu_sample(layers)
+        times.append(dt * total / fl)                 # seconds the full workload would take
+    t_full = float(np.mean(times))
+    value = n_te / t_full
+    cores = os.cpu_count() or 1
+    sample = f"1 of {N_EST} estimators (T=27), {layers} of {L} layers per step, scaled by algorithmic FLOPs"
+    line = {
+        "impl": "reference", "metric": "test rows/sec predict_proba", "value": value, "unit": "rows/s",
+        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": t_full * 1e3,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": f"{WORKLOAD}: {n_tr} train / {n_te} test rows, 21 feats + 768-d image emb, "
+                               f"{N_EST} estimators, reference-equivalent (context rebuilt per call)"},
+        "cpu_baseline": {"value": value, "unit": "rows/s", "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": value, "unit": "rows/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+# --------------------------------------------------------------------------------------------
+# GPU arm
+# --------------------------------------------------------------------------------------------
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+    from multimodalpfn_b200 import _lib
+    from multimodalpfn_b200.classifier import MMPFNClassifier
+    from multimodalpfn_b200.engine import proba_from_logits
+    from multimodalpfn_b200.synth import Geometry, make_dataset, make_state_dict
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+
+    peaks = load_peaks()
+    geom = Geometry(mgm_heads=8, cap_heads=8)
+    sd = make_state_dict(geom, seed=1)
+    d = make_dataset(WORKLOAD, 0)
+    n_tr, n_te = len(d["y_train"]), len(d["y_test"])
+    # weak scaling: rank r classifies its own copy-sized chunk of test rows (distinct rows per rank)
+    rng = np.random.default_rng(100 + rank)
+    X_test = d["X_test"] if rank == 0 else d["X_test"][rng.permutation(n_te)]
+    img_test = d["img_test"] if rank == 0 else rng.standard_normal(d["img_test"].shape).astype(np.float32)
+
+    clf = MMPFNClassifier(mixer_type="MGM+CAP", mgm_heads=8, cap_heads=8, features_per_group=2, n_estimators=N_EST,
+                          model_path=(sd, geom), device=f"cuda:{local}", inference_precision=args.precision,
+                          ignore_pretraining_limits=True, random_state=0)
+    clf.fit(d["X_train"], d["img_train"], d["y_train"])
+    eng = clf.executor_
+    if world > 1:
+        from multimodalpfn_b200.dist import ShardedEngine
+        eng = ShardedEngine(eng, rank, world)
+        clf.executor_ = eng
+    Ts = sorted({(g["F"] + 1) // 2 + 8 + 1 for g in eng.groups}, reverse=True)
+
+    # ---- device-resident step -------------------------------------------------------------------
+    X_tests_host = [m.transform(X_test) for m in clf.members_]
+    staged = eng.stage(X_tests_host, img_test)
+    perms = [m.class_perm for m in clf.members_]
+
+    def step_device():
+        lg = eng.logits_staged(staged)
+        return lg
+
+    flush = torch.empty(384 * 1024 * 1024, dtype=torch.uint8, device=dev)   # > 126 MB L2
+
+    def sync_all():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(args.warmup):
+        step_device()
+    sync_all()
+    l0 = _lib.launch_count()
+    evs = []
+    with ClockSampler(local) as clocks:
+        sync_all()
+        t_wall0 = time.perf_counter()
+        for _ in range(args.steps):
+            flush.zero_()                              # L2 flush between timed iterations (not timed)
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record()
+            lg = step_device()
+            b.record()
+            evs.append((a, b))
+        sync_all()
+        t_wall = time.perf_counter() - t_wall0
+    launches = (_lib.launch_count() - l0) // max(args.steps, 1)
+    ms = float(np.mean([a.elapsed_time(b) for a, b in evs]))
+    if world > 1:
+        tms = torch.tensor([ms], device=dev)
+        dist.all_reduce(tms, op=dist.ReduceOp.MAX)
+        ms = float(tms.item())
+    value = world * n_te / (ms * 1e-3)
+    proba_dev = proba_from_logits(lg, perms, n_classes=clf.n_classes_)
+    assert np.allclose(proba_dev.sum(1), 1.0, atol=1e-5)
+
+    # ---- end-to-end step through the public API, host buffers ----------------------------------
+    for _ in range(max(1, min(args.warmup, 3))):
+        clf.predict_proba(X_test, img_test)
+    sync_all()
+    e2e_times = []
+    for _ in range(args.steps):
+        flush.zero_()
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        p = clf.predict_proba(X_test, img_test)       # ends with the D2H copy of the probabilities
+        e2e_times.append(time.perf_counter() - t0)
+    e2e_s = float(np.mean(e2e_times))
+    if world > 1:
+        te = torch.tensor([e2e_s], device=dev)
+        dist.all_reduce(te, op=dist.ReduceOp.MAX)
+        e2e_s = float(te.item())
+    h2d = sum(x.nbytes for x in X_tests_host) + img_test.nbytes
+    d2h = p.nbytes
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    # ---- roofline of the dominant kernel: item-axis attention (train rows, T=27 group) ---------
+    roof = roofline_item_attention(torch, _lib, dev, n_tr, Ts[0], N_EST // 2, peaks)
+    extra = kernel_breakdown(torch, _lib, dev, n_tr + n_te, Ts[0], N_EST // 2, peaks)
+
+    # ---- CPU baseline on the host cores (bounded sample) ----------------------------------------
+    total, _, _ = full_flops()
+    cpu = None
+    if args.cpu_baseline:
+        t1, f1, _ = cpu_sample(1)
+        layers = int(max(1, min(L, 20.0 // max(t1, 1e-3))))
+        dt, fl, _ = cpu_sample(layers)
+        cpu = {"value": n_te / (dt * total / fl), "unit": "rows/s", "cores": os.cpu_count() or 1, "kind": "port",
+               "sample": f"oracle (fp32 torch CPU) on 1 of {N_EST} estimators (T=27), {layers} of {L} layers, "
+                         f"{dt:.1f} s measured, scaled by algorithmic FLOPs"}
+
+    line = {
+        "metric": "test rows/sec predict_proba", "value": value, "unit": "rows/s", "n_gpus": world,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": args.precision, "data": "synthetic",
+        "config": {"workload": f"{WORKLOAD}: {n_tr} train / {n_te} test rows per GPU, 21 feats + 768-d image emb, "
+                               f"{N_EST} estimators (T={Ts}), MGM8+CAP8, 12 layers, emsize 192, random-init weights; "
+                               "reference-equivalent: train context rebuilt inside every call",
+                   "l2": "flushed between timed iterations (384 MB memset)",
+                   "algorithmic_tflop_per_step": total / 1e12},
+        "achieved_tflops": total / (ms * 1e-3) / 1e12 if world == 1 else None,
+        "e2e": {"value": world * n_te / e2e_s, "unit": "rows/s", "h2d_bytes_per_step": int(h2d),
+                "d2h_bytes_per_step": int(d2h), "ms_per_step": e2e_s * 1e3},
+        "gpu_launches": int(launches),
+        "clocks": clocks.summary(),
+        "roofline": roof,
+        "kernels": extra,
+        "cpu_baseline": cpu,
+        "wall_ms_per_step_incl_flush": t_wall * 1e3 / max(args.steps, 1),
+        "peaks": peaks,
+    }
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def _time_kernel(torch, fn, iters=20, warm=3):
+    for _ in range(warm):
+        fn()
+    torch.cuda.synchronize()
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    a.record()
+    for _ in range(iters):
+        fn()
+    b.record()
+    torch.cuda.synchronize()
+    return a.elapsed_time(b) / iters
+
+
+def roofline_item_attention(torch, _lib, dev, n_tr, T, B, peaks):
+    """The item-axis attention kernel alone at the workload's train-row shape (B estimators x T
+    token columns x 6 heads, n_q = n_kv = Ntr, d = 32).  Inputs (3 x 83 MB at T=27, B=4) exceed
+    what stays hot per CTA wave but fit L2; the kernel is compute (tensor/MUFU) bound."""
+    lib = _lib.load()
+    pad = (n_tr + 63) // 64 * 64
+    planes = B * T * NH
+    g = torch.Generator(device=dev).manual_seed(0)
+    q = torch.randn(planes, pad, DK, device=dev, generator=g).to(torch.bfloat16)
+    k = torch.randn(planes, pad, DK, device=dev, generator=g).to(torch.bfloat16)
+    vt = torch.randn(planes, DK, pad, device=dev, generator=g).to(torch.bfloat16)
+    out = torch.empty(B, n_tr, T, E, device=dev, dtype=torch.bfloat16)
+    st = torch.cuda.current_stream().cuda_stream
+
+    def run():
+        _lib.check(lib.mmpfn_item_attention_bf16(q.data_ptr(), k.data_ptr(), vt.data_ptr(), B, T, n_tr, pad, n_tr, pad,
+                                                 0, out.data_ptr(), st), "item_attention")
+    ms = _time_kernel(torch, run)
+    fl = flops_item_attention(n_tr, n_tr, T, B)
+    ach = fl / (ms * 1e-3) / 1e12
+    return {"kernel": "tc_item_attn_kernel", "bound": "tensor", "achieved": ach, "peak": peaks["burst"],
+            "unit": "TFLOP/s", "frac": ach / peaks["burst"], "traffic": None, "ms_per_launch": ms,
+            "flops_per_launch": fl, "peak_source": f"{peaks['src']} bf16 burst (kernel timed alone)",
+            "note": "d=32: 128 tensor FLOP per exp2; MUFU bound = 16 exp/clk/SM"}
+
+
+def kernel_breakdown(torch, _lib, dev, S, T, B, peaks):
+    """Isolated timings of the GEMM shapes of one layer (B estimators, S rows, T tokens)."""
+    lib = _lib.load()
+    M = B * S * T
+    st = torch.cuda.current_stream().cuda_stream
+    res = {}
+    g = torch.Generator(device=dev).manual_seed(1)
+    for name, (N, K, epi) in {"qkv_proj": (576, 192, 0), "mlp_up_gelu": (768, 192, 1)}.items():
+        A = torch.randn(M, K, device=dev, generator=g).to(torch.bfloat16)
+        W = torch.randn(N, K, device=dev, generator=g).to(torch.bfloat16)
+        O = torch.empty(M, N, device=dev, dtype=torch.bfloat16)
+
+        def run():
+            _lib.check(lib.mmpfn_linear_bf16(A.data_ptr(), W.data_ptr(), M, N, K, epi, O.data_ptr(), st), name)
+        ms = _time_kernel(torch, run)
+        fl = 2.0 * M * N * K
+        by = 2.0 * (M * K + N * K + M * N)
+        res[name] = {"ms": ms, "tflops": fl / ms / 1e9, "frac_tensor": fl / ms / 1e9 / peaks["burst"],
+                     "gbs": by / ms / 1e6, "frac_hbm": by / ms / 1e6 / peaks["hbm"], "M": M, "N": N, "K": K}
+    # LayerNorm (+residual) stand-alone: the bandwidth-bound reference point
+    x = torch.randn(M, E, device=dev, generator=g)
+    r = torch.randn(M, E, device=dev, generator=g)
+    y = torch.empty_like(x)
+    yb = torch.empty(M, E, device=dev, dtype=torch.bfloat16)
+
+    def run_ln():
+        _lib.check(lib.mmpfn_layernorm(x.data_ptr(), r.data_ptr(), None, None, M, E, y.data_ptr(), yb.data_ptr(), st),
+                   "layernorm")
+    ms = _time_kernel(torch, run_ln)
+    by = M * E * (4 + 4 + 4 + 2)
+    res["layernorm_residual"] = {"ms": ms, "gbs": by / ms / 1e6, "frac_hbm": by / ms / 1e6 / peaks["hbm"],
+                                 "bytes": by, "note": "working set fits L2 at this shape"}
+    return res
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--precision", default="bf16", choices=["bf16", "fp32"])
+    ap.add_argument("--no-cpu-baseline", dest="cpu_baseline", action="store_false")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "ours" else args.warmup
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -181,6 +181,13 @@ int mmpfn_linear_f32(const float* A, const float* W, const float* bias, int M, i
 int mmpfn_linear_bf16(const uint16_t* A, const uint16_t* W, int M, int N, int K, int epi, uint16_t* out,
                       void* stream);
 
+/* Item-axis attention alone (layer.py:341-379), bf16 tcgen05 kernel, for unit tests and roofline timing.
+ *   q  [B*T*nhead][Sq_pad][32]   k [planes_kv][Skv_pad][32]   vt [planes_kv][32][Skv_pad]   (bf16)
+ *   planes_kv = B*T (shared_kv = 1: every query head reads head 0) or B*T*nhead (shared_kv = 0)
+ *   out [B][n_q][T][nhead*32] bf16.  Sq_pad/Skv_pad are the allocated row counts (multiples of 8). */
+int mmpfn_item_attention_bf16(const uint16_t* q, const uint16_t* k, const uint16_t* vt, int B, int T, int n_q,
+                              int Sq_pad, int n_kv, int Skv_pad, int shared_kv, uint16_t* out, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

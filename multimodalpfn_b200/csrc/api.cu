@@ -505,4 +505,18 @@ int mmpfn_linear_bf16(const uint16_t* A, const uint16_t* W, int M, int N, int K,
   return launch_tc_gemm(a, (cudaStream_t)stream);
 }
 
+int mmpfn_item_attention_bf16(const uint16_t* q, const uint16_t* k, const uint16_t* vt, int B, int T, int n_q,
+                              int Sq_pad, int n_kv, int Skv_pad, int shared_kv, uint16_t* out, void* stream) {
+  MMPFN_TRY(require_device());
+  if (!q || !k || !vt || !out || B < 1 || T < 1 || n_q < 1 || n_kv < 1 || Sq_pad < n_q || Skv_pad < n_kv ||
+      Sq_pad % 8 || Skv_pad % 8) {
+    set_error("item_attention_bf16: bad arguments");
+    return MMPFN_EINVAL;
+  }
+  TcItemAttn a{};
+  a.q = q; a.k = k; a.vt = vt; a.out = out; a.B = B; a.T = T; a.n_q = n_q; a.Sq_pad = Sq_pad; a.n_kv = n_kv;
+  a.Skv_pad = Skv_pad; a.shared_kv = shared_kv;
+  return launch_tc_item_attn(a, (cudaStream_t)stream);
+}
+
 }  // extern "C"

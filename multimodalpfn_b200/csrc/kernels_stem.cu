@@ -122,16 +122,22 @@ __global__ void __launch_bounds__(256) tab_fit_kernel(const float* __restrict__ 
         fill = (float)(s / c);
       }
       auto x1 = [&](int i) { return fill_bad(raw(i), fill); };
-      // 3. two-pass n_sigma bounds (encoders.py:145-158)
-      float mu, sd;
-      nan_mean_std(x1, n_train, mu, sd, sh);
-      float cut = sd * n_sigma;
-      const float lo1 = mu - cut, hi1 = mu + cut;
-      auto x1m = [&](int i) { const float v = x1(i); return (v > hi1 || v < lo1) ? CUDART_NAN_F : v; };
-      nan_mean_std(x1m, n_train, mu, sd, sh);
-      cut = sd * n_sigma;
-      lo = mu - cut;
-      hi = mu + cut;
+      // 3. two-pass n_sigma bounds (encoders.py:145-158); n_sigma <= 0 or inf = step switched off
+      //    (InferenceConfig.remove_outliers False, model/config.py:43): bounds at -inf/+inf are a no-op
+      if (n_sigma > 0.f && !isinf(n_sigma)) {
+        float mu, sd;
+        nan_mean_std(x1, n_train, mu, sd, sh);
+        float cut = sd * n_sigma;
+        const float lo1 = mu - cut, hi1 = mu + cut;
+        auto x1m = [&](int i) { const float v = x1(i); return (v > hi1 || v < lo1) ? CUDART_NAN_F : v; };
+        nan_mean_std(x1m, n_train, mu, sd, sh);
+        cut = sd * n_sigma;
+        lo = mu - cut;
+        hi = mu + cut;
+      } else {
+        lo = -CUDART_INF_F;
+        hi = CUDART_INF_F;
+      }
       // 4. z-norm statistics of the soft-clipped train rows (encoders.py:81-88)
       const float lo2 = lo, hi2 = hi;
       auto x2 = [&](int i) { return soft_clip(x1(i), lo2, hi2); };

@@ -99,43 +99,50 @@ class B200InferenceEngine:
             if self.img_train_dev is not None:
                 g["ctx"].n_tok = self.img_train_dev.shape[1]
 
-    def logits(self, X_test_per_member: Sequence[Optional[np.ndarray]], image_test: Optional[np.ndarray]) -> torch.Tensor:
-        """-> [n_est, Nte, n_out] on the device, estimator order as given to the constructor."""
-        m = self.model
-        dev = m.device
-        n_est = len(self.members)
+    def stage(self, X_test_per_member: Sequence[Optional[np.ndarray]], image_test: Optional[np.ndarray]):
+        """Host -> device copies of one call's inputs (the per-step H2D traffic): the preprocessed test
+        table of every estimator and the test embeddings."""
+        dev = self.model.device
         img_test_dev = None
         if image_test is not None and self.img_train_dev is not None:        # inference.py:311-316
             img_test_dev = torch.as_tensor(np.asarray(image_test, dtype=np.float32)).to(dev, non_blocking=True)
             if img_test_dev.dim() == 2:
                 img_test_dev = img_test_dev[:, None]
-        out = [None] * n_est
+        Xte = []
+        for g in self.groups:
+            if g["F"] >= 0:
+                Xte.append(torch.from_numpy(np.stack([np.asarray(X_test_per_member[i], dtype=np.float32)
+                                                      for i in g["idx"]])).to(dev, non_blocking=True))
+            else:
+                Xte.append(None)
+        return dict(X_test=Xte, img_test=img_test_dev)
+
+    def logits_staged(self, staged) -> torch.Tensor:
+        """The device-resident part of one call -> [n_est, Nte, n_out], estimator order as given to
+        the constructor."""
+        m = self.model
+        out = [None] * len(self.members)
+        img_test_dev = staged["img_test"]
         if self.cache_context:
             tok_test = m.stem_image(img_test_dev) if img_test_dev is not None else None
-            for g in self.groups:
-                Xte = None
-                if g["F"] >= 0:
-                    Xte = torch.from_numpy(np.stack([np.asarray(X_test_per_member[i], dtype=np.float32)
-                                                     for i in g["idx"]])).to(dev, non_blocking=True)
+            for g, Xte in zip(self.groups, staged["X_test"]):
                 lg = m.predict_with_context(g["ctx"], Xte, None, img_tok_test=tok_test)
                 for k, i in enumerate(g["idx"]):
                     out[i] = lg[k]
         else:
             # reference-equivalent: the train context is rebuilt inside every call (inference.py:302-348)
-            img_full = None
+            tok = None
             if img_test_dev is not None:
-                img_full = torch.cat([self.img_train_dev, img_test_dev], dim=0)
-            tok = m.stem_image(img_full) if img_full is not None else None
-            for g in self.groups:
+                tok = m.stem_image(torch.cat([self.img_train_dev, img_test_dev], dim=0))
+            for g, Xte in zip(self.groups, staged["X_test"]):
                 n_tr = g["y_train"].shape[1]
-                Xte = X_full = None
-                if g["F"] >= 0:
-                    Xte = torch.from_numpy(np.stack([np.asarray(X_test_per_member[i], dtype=np.float32)
-                                                     for i in g["idx"]])).to(dev, non_blocking=True)
-                    X_full = torch.cat([g["X_train"], Xte], dim=1)
+                X_full = None if Xte is None else torch.cat([g["X_train"], Xte], dim=1)
                 ctx = m.fit_context(g["X_train"], None, g["y_train"], X_all=X_full,
                                     img_tok_train=None if tok is None else tok[:n_tr], check=False)
                 lg = m.predict_with_context(ctx, Xte, None, img_tok_test=None if tok is None else tok[n_tr:])
                 for k, i in enumerate(g["idx"]):
                     out[i] = lg[k]
         return torch.stack(out)
+
+    def logits(self, X_test_per_member: Sequence[Optional[np.ndarray]], image_test: Optional[np.ndarray]) -> torch.Tensor:
+        return self.logits_staged(self.stage(X_test_per_member, image_test))

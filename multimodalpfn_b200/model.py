@@ -254,7 +254,7 @@ class B200PerFeatureTransformer:
             B, n_train = y_train.shape
             F = 0 if X_train is None else X_train.shape[2]
             n_tok = 0 if img_train is None else img_train.shape[1]
-            if X_train is None and img_train is None:
+            if X_train is None and img_train is None and img_tok_train is None:
                 raise ValueError("need tabular features, image embeddings, or both")
             stats = None
             if X_train is not None:

@@ -1,0 +1,109 @@
+"""Host-side ensemble preprocessing in front of the hot path.
+
+Written from scratch; it plays the role of the reference's ``EnsembleConfig`` generation and
+``fit_preprocessing`` (``preprocessing.py:228-335, 501-633``; transforms in
+``model/preprocessing.py``) with the same structure — ``n_estimators`` members alternate between
+two recipes, each with its own feature permutation and class permutation — but it is NOT a
+bit-level replica of that CPU pipeline (which is out of the hot path and would be reused
+unchanged in the plug-in integration).  Recipes:
+
+* ``"none"``            — columns as they are (what the authors run: ``run.py:101-104``);
+* ``"quantile_svd"``    — originals + uniform quantile transform of the numeric columns +
+                          truncated-SVD components (the shape of the reference's first default
+                          recipe, ``preprocessing.py:141-149``).
+
+A deterministic row-fingerprint column is appended when ``fingerprint`` is on (the reference
+uses Python ``hash`` — process dependent, SURVEY.md gotcha 3; here blake2b).
+"""
+from __future__ import annotations
+
+import dataclasses
+import hashlib
+from typing import Optional
+
+import numpy as np
+
+__all__ = ["EnsembleMember", "make_members", "RECIPES"]
+
+RECIPES = ("quantile_svd", "none")
+
+
+def _fingerprint(X: np.ndarray) -> np.ndarray:
+    out = np.empty(X.shape[0], dtype=np.float32)
+    Xc = np.ascontiguousarray(X, dtype=np.float32)
+    for i in range(Xc.shape[0]):
+        h = hashlib.blake2b(Xc[i].tobytes(), digest_size=8).digest()
+        out[i] = (int.from_bytes(h, "little") % (1 << 24)) / float(1 << 24)
+    return out
+
+
+@dataclasses.dataclass
+class EnsembleMember:
+    recipe: str
+    feature_shift_seed: Optional[int]      # None = keep the column order
+    class_perm: Optional[np.ndarray]       # logits are gathered with it (classifier.py:550-551)
+    fingerprint: bool
+    feature_perm: Optional[np.ndarray] = None
+    numeric_cols: Optional[np.ndarray] = None
+    _qt: object = None
+    _svd: object = None
+    _svd_mean: Optional[np.ndarray] = None
+    _svd_scale: Optional[np.ndarray] = None
+
+    def fit_transform(self, X: Optional[np.ndarray], y: np.ndarray):
+        """-> (X_train' or None, y_train permuted)."""
+        y_out = y if self.class_perm is None else self.class_perm[y]      # preprocessing.py:540-541
+        if X is None:
+            return None, y_out.astype(np.float32)
+        return self._apply(X, fit=True), y_out.astype(np.float32)
+
+    def transform(self, X: Optional[np.ndarray]):
+        return None if X is None else self._apply(X, fit=False)
+
+    def _apply(self, X: np.ndarray, fit: bool) -> np.ndarray:
+        X = np.asarray(X, dtype=np.float32)
+        parts = [X]
+        if self.recipe == "quantile_svd":
+            from sklearn.decomposition import TruncatedSVD
+            from sklearn.preprocessing import QuantileTransformer
+            n, F = X.shape
+            if fit:
+                nun = np.array([len(np.unique(X[~np.isnan(X[:, j]), j])) for j in range(F)])
+                self.numeric_cols = np.where(nun > 30)[0]
+            if len(self.numeric_cols):
+                Xn = X[:, self.numeric_cols]
+                if fit:
+                    self._qt = QuantileTransformer(n_quantiles=max(min(n // 10, 1000), 2),
+                                                   output_distribution="uniform", random_state=0)
+                    self._qt.fit(Xn)
+                parts.append(self._qt.transform(Xn).astype(np.float32))
+            k = max(1, min(n // 10 + 1, F // 2)) if fit else self._svd.n_components
+            Xz = np.nan_to_num(np.concatenate(parts, 1), nan=0.0, posinf=0.0, neginf=0.0)
+            if fit:
+                self._svd_mean = Xz.mean(0)
+                self._svd_scale = Xz.std(0) + 1e-6
+                self._svd = TruncatedSVD(n_components=k, algorithm="arpack", random_state=0)
+                self._svd.fit((Xz - self._svd_mean) / self._svd_scale)
+            parts.append(self._svd.transform((Xz - self._svd_mean) / self._svd_scale).astype(np.float32))
+        out = np.concatenate(parts, 1)
+        if self.fingerprint:
+            out = np.concatenate([out, _fingerprint(X)[:, None]], 1)
+        if self.feature_shift_seed is not None:
+            if fit:
+                self.feature_perm = np.random.default_rng(self.feature_shift_seed).permutation(out.shape[1])
+            out = out[:, self.feature_perm]
+        return np.ascontiguousarray(out, dtype=np.float32)
+
+
+def make_members(n_estimators: int, n_features: int, n_classes: int, rng: np.random.Generator, *,
+                 recipes=RECIPES, fingerprint: bool = True, feature_shift: bool = True, class_shift: bool = True):
+    """Balanced mix of the recipes, each with its own feature / class permutation
+    (the structure of ``EnsembleConfig.generate_for_classification``, ``preprocessing.py:228-335``)."""
+    members = []
+    for e in range(n_estimators):
+        recipe = recipes[e * len(recipes) // max(n_estimators, 1)] if n_estimators >= len(recipes) else recipes[e % len(recipes)]
+        fseed = int(rng.integers(0, 2**31 - 1)) if feature_shift and n_features > 0 else None
+        cperm = rng.permutation(n_classes) if class_shift else None
+        members.append(EnsembleMember(recipe=recipe, feature_shift_seed=fseed, class_perm=cperm,
+                                      fingerprint=fingerprint))
+    return members

@@ -6,7 +6,7 @@ mkdir -p gpurun_out
 run() {  # name timeout pytest-args...
   local name=$1; local to=$2; shift 2
   echo "=== $name" | tee -a gpurun_out/probe_summary.log
-  timeout -k 5 "$to" python -m pytest "$@" -q -x --no-header -p no:cacheprovider > "gpurun_out/probe_$name.log" 2>&1
+  timeout -k 5 "$to" python -m pytest "$@" -q --no-header -p no:cacheprovider > "gpurun_out/probe_$name.log" 2>&1
   local rc=$?
   echo "rc=$rc $(tail -n 1 gpurun_out/probe_$name.log)" | tee -a gpurun_out/probe_summary.log
   grep -E "^(FAILED|ERROR)|Error|error:|assert|mbarrier timeout" "gpurun_out/probe_$name.log" | head -n 12 | tee -a gpurun_out/probe_summary.log
