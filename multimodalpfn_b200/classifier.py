@@ -173,10 +173,12 @@ class MMPFNClassifier(ClassifierMixin, BaseEstimator):
             if image_test.ndim == 2:
                 image_test = image_test[:, None]
         logits = self.executor_.logits(X_tests, image_test)
-        return proba_from_logits(logits, [m.class_perm for m in self.members_], n_classes=self.n_classes_,
-                                 class_counts=self.class_counts_, softmax_temperature=self.softmax_temperature,
-                                 average_before_softmax=self.average_before_softmax,
-                                 balance_probabilities=self.balance_probabilities)
+        proba = proba_from_logits(logits, [m.class_perm for m in self.members_], n_classes=self.n_classes_,
+                                  class_counts=self.class_counts_, softmax_temperature=self.softmax_temperature,
+                                  average_before_softmax=self.average_before_softmax,
+                                  balance_probabilities=self.balance_probabilities)
+        self.executor_.check_nan()      # transformer.py:727-731, :790-796 (one flag read after the D2H copy)
+        return proba
 
     def predict(self, X, X_image):
         proba = self.predict_proba(X, X_image)

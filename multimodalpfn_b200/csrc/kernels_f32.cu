@@ -268,11 +268,175 @@ int launch_feat_attn(const TIn* qkv, TOut* att, long long n_seq, int T, cudaStre
 }
 }  // namespace
 
+// ---------------------------------------------------------------------------------------------
+// Attention between features, bf16 tensor-core version (mma.sync m16n8k16, fp32 accumulate).
+// One CTA per table row: the row's whole qkv block ([T][576] bf16, contiguous in HBM) is staged in
+// shared memory once (16 B cp.async, rows padded to 1168 B so that ldmatrix is conflict free), then
+// each warp owns (head, 16-query tile) work items: S = Q K^T in registers, softmax in registers,
+// P re-used as the A fragments of O = P V.  HBM-bound: reads qkv once, writes att once.
+// ---------------------------------------------------------------------------------------------
+namespace {
+constexpr int FA_ROW_BYTES = 3 * kE * 2 + 16;   // 1168
+
+__device__ __forceinline__ void ldsm_x4(uint32_t (&r)[4], uint32_t addr) {
+  asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0,%1,%2,%3}, [%4];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(addr));
+}
+__device__ __forceinline__ void ldsm_x4_t(uint32_t (&r)[4], uint32_t addr) {
+  asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0,%1,%2,%3}, [%4];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(addr));
+}
+__device__ __forceinline__ void mma_bf16(float (&d)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
+  asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+               : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
+               : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+
+// KT = number of 16-key tiles the register file is sized for (T <= 16*KT)
+template <int KT>
+__global__ void __launch_bounds__(384) feat_attn_mma_kernel(const uint16_t* __restrict__ qkv,
+                                                            uint16_t* __restrict__ att, int T) {
+  extern __shared__ __align__(16) uint8_t fsm[];
+  const long long row = blockIdx.x;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int n_kt = (T + 15) >> 4;               // 16-key tiles actually present
+  const int Tp = n_kt * 16;
+  const uint32_t sbase = (uint32_t)__cvta_generic_to_shared(fsm);
+
+  // stage [T][576] bf16 -> smem rows of FA_ROW_BYTES; zero the padded token rows
+  const uint8_t* src = reinterpret_cast<const uint8_t*>(qkv + row * T * (3 * kE));
+  constexpr int CH = 3 * kE * 2 / 16;           // 72 chunks of 16 B per token
+  for (int i = threadIdx.x; i < T * CH; i += blockDim.x) {
+    const int t = i / CH, c = i % CH;
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(sbase + t * FA_ROW_BYTES + c * 16),
+                 "l"(src + (long long)t * (3 * kE * 2) + c * 16));
+  }
+  for (int i = threadIdx.x; i < (Tp - T) * CH; i += blockDim.x) {
+    const int t = T + i / CH, c = i % CH;
+    *reinterpret_cast<uint4*>(fsm + t * FA_ROW_BYTES + c * 16) = make_uint4(0, 0, 0, 0);
+  }
+  asm volatile("cp.async.commit_group;");
+  asm volatile("cp.async.wait_group 0;");
+  __syncthreads();
+
+  const float c2 = 0.17677669529663687f * 1.4426950408889634f;   // log2(e)/sqrt(d)
+  const int n_items = kH * n_kt;
+  for (int item = warp; item < n_items; item += (blockDim.x >> 5)) {
+    const int h = item / n_kt, mt = item % n_kt;
+    // Q fragments: 16 queries x 32 d = 2 k-steps
+    uint32_t qa[2][4];
+#pragma unroll
+    for (int ks = 0; ks < 2; ++ks)
+      ldsm_x4(qa[ks], sbase + (mt * 16 + (lane & 15)) * FA_ROW_BYTES + (h * kD + ks * 16 + (lane >> 4) * 8) * 2);
+    // S = Q K^T
+    float sacc[2 * KT][4];
+#pragma unroll
+    for (int nt = 0; nt < 2 * KT; ++nt) { sacc[nt][0] = sacc[nt][1] = sacc[nt][2] = sacc[nt][3] = 0.f; }
+#pragma unroll
+    for (int kt = 0; kt < KT; ++kt) {
+      if (kt < n_kt) {
+#pragma unroll
+        for (int ks = 0; ks < 2; ++ks) {
+          uint32_t kb[4];
+          const int mi = lane >> 3;
+          ldsm_x4(kb, sbase + (kt * 16 + (mi >> 1) * 8 + (lane & 7)) * FA_ROW_BYTES +
+                          (kE + h * kD + ks * 16 + (mi & 1) * 8) * 2);
+          mma_bf16(sacc[2 * kt], qa[ks], kb[0], kb[1]);
+          mma_bf16(sacc[2 * kt + 1], qa[ks], kb[2], kb[3]);
+        }
+      }
+    }
+    // softmax over the T real keys; thread holds rows (lane/4) and (lane/4 + 8), key columns (lane%4)*2 + {0,1}
+    float mx0 = -INFINITY, mx1 = -INFINITY;
+#pragma unroll
+    for (int nt = 0; nt < 2 * KT; ++nt) {
+      if (nt < 2 * n_kt) {
+        const int key = nt * 8 + (lane & 3) * 2;
+        if (key >= T) { sacc[nt][0] = -INFINITY; sacc[nt][2] = -INFINITY; }
+        if (key + 1 >= T) { sacc[nt][1] = -INFINITY; sacc[nt][3] = -INFINITY; }
+        mx0 = fmaxf(mx0, fmaxf(sacc[nt][0], sacc[nt][1]));
+        mx1 = fmaxf(mx1, fmaxf(sacc[nt][2], sacc[nt][3]));
+      }
+    }
+    mx0 = fmaxf(mx0, __shfl_xor_sync(0xffffffffu, mx0, 1));
+    mx0 = fmaxf(mx0, __shfl_xor_sync(0xffffffffu, mx0, 2));
+    mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, 1));
+    mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, 2));
+    const float mc0 = mx0 * c2, mc1 = mx1 * c2;
+    float l0 = 0.f, l1 = 0.f;
+    float oacc[4][4];
+#pragma unroll
+    for (int nt = 0; nt < 4; ++nt) { oacc[nt][0] = oacc[nt][1] = oacc[nt][2] = oacc[nt][3] = 0.f; }
+#pragma unroll
+    for (int kt = 0; kt < KT; ++kt) {
+      if (kt < n_kt) {
+        uint32_t pa[4];
+        {
+          const float p00 = fast_exp2f(fmaf(sacc[2 * kt][0], c2, -mc0)), p01 = fast_exp2f(fmaf(sacc[2 * kt][1], c2, -mc0));
+          const float p10 = fast_exp2f(fmaf(sacc[2 * kt][2], c2, -mc1)), p11 = fast_exp2f(fmaf(sacc[2 * kt][3], c2, -mc1));
+          const float q00 = fast_exp2f(fmaf(sacc[2 * kt + 1][0], c2, -mc0)), q01 = fast_exp2f(fmaf(sacc[2 * kt + 1][1], c2, -mc0));
+          const float q10 = fast_exp2f(fmaf(sacc[2 * kt + 1][2], c2, -mc1)), q11 = fast_exp2f(fmaf(sacc[2 * kt + 1][3], c2, -mc1));
+          l0 += (p00 + p01) + (q00 + q01);
+          l1 += (p10 + p11) + (q10 + q11);
+          pa[0] = pack_bf16x2(p00, p01); pa[1] = pack_bf16x2(p10, p11);
+          pa[2] = pack_bf16x2(q00, q01); pa[3] = pack_bf16x2(q10, q11);
+        }
+        // V fragments (transposed load): 16 keys x 32 d = 4 n-tiles
+#pragma unroll
+        for (int np = 0; np < 2; ++np) {
+          uint32_t vb[4];
+          const int mi = lane >> 3;
+          ldsm_x4_t(vb, sbase + (kt * 16 + (mi & 1) * 8 + (lane & 7)) * FA_ROW_BYTES +
+                            (2 * kE + h * kD + np * 16 + (mi >> 1) * 8) * 2);
+          mma_bf16(oacc[2 * np], pa, vb[0], vb[1]);
+          mma_bf16(oacc[2 * np + 1], pa, vb[2], vb[3]);
+        }
+      }
+    }
+    l0 += __shfl_xor_sync(0xffffffffu, l0, 1);
+    l0 += __shfl_xor_sync(0xffffffffu, l0, 2);
+    l1 += __shfl_xor_sync(0xffffffffu, l1, 1);
+    l1 += __shfl_xor_sync(0xffffffffu, l1, 2);
+    const float i0 = 1.0f / l0, i1 = 1.0f / l1;
+    const int q0 = mt * 16 + (lane >> 2), q1 = q0 + 8;
+    uint16_t* o0 = att + (row * T + q0) * kE + h * kD + (lane & 3) * 2;
+    uint16_t* o1 = att + (row * T + q1) * kE + h * kD + (lane & 3) * 2;
+#pragma unroll
+    for (int nt = 0; nt < 4; ++nt) {
+      if (q0 < T) *reinterpret_cast<uint32_t*>(o0 + nt * 8) = pack_bf16x2(oacc[nt][0] * i0, oacc[nt][1] * i0);
+      if (q1 < T) *reinterpret_cast<uint32_t*>(o1 + nt * 8) = pack_bf16x2(oacc[nt][2] * i1, oacc[nt][3] * i1);
+    }
+  }
+}
+
+template <int KT>
+int launch_feat_attn_mma_t(const uint16_t* qkv, uint16_t* att, long long n_seq, int T, cudaStream_t st) {
+  const int Tp = (T + 15) / 16 * 16;
+  const size_t smem = (size_t)Tp * FA_ROW_BYTES;
+  auto kern = feat_attn_mma_kernel<KT>;
+  static bool configured = false;
+  if (!configured) {
+    cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, KT * 16 * FA_ROW_BYTES);
+    configured = true;
+  }
+  const int n_items = kH * (Tp / 16);
+  const int warps = n_items < 12 ? n_items : 12;
+  kern<<<(unsigned)n_seq, warps * 32, smem, st>>>(qkv, att, T);
+  return count_launch();
+}
+}  // namespace
+
 int launch_feat_attn_f32(const float* qkv, float* att, long long n_seq, int T, cudaStream_t st) {
   return launch_feat_attn<float, float>(qkv, att, n_seq, T, st);
 }
 int launch_feat_attn_bf16(const uint16_t* qkv, uint16_t* att, long long n_seq, int T, cudaStream_t st) {
-  return launch_feat_attn<uint16_t, uint16_t>(qkv, att, n_seq, T, st);
+  if (n_seq <= 0) return MMPFN_OK;
+  if (T <= 32) return launch_feat_attn_mma_t<2>(qkv, att, n_seq, T, st);
+  if (T <= 64) return launch_feat_attn_mma_t<4>(qkv, att, n_seq, T, st);
+  if (T <= 96) return launch_feat_attn_mma_t<6>(qkv, att, n_seq, T, st);
+  if (T <= 144) return launch_feat_attn_mma_t<9>(qkv, att, n_seq, T, st);
+  if (T <= 192) return launch_feat_attn_mma_t<12>(qkv, att, n_seq, T, st);
+  return launch_feat_attn<uint16_t, uint16_t>(qkv, att, n_seq, T, st);   // CUDA-core fallback for very wide rows
 }
 
 // ---------------------------------------------------------------------------------------------

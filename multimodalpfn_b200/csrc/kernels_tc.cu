@@ -44,13 +44,21 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
       : "memory");
   return ok != 0;
 }
+__device__ __noinline__ void mbar_timeout() {
+  printf("mmpfn: mbarrier timeout (block %d,%d thread %d)\n", blockIdx.x, blockIdx.y, threadIdx.x);
+  __trap();
+}
+// try_wait suspends the thread in hardware for a bounded time per call; the clock is only consulted
+// every 2^14 failed probes so that the spinning producer / MMA lanes do not eat issue slots.
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   if (mbar_try_wait(bar, parity)) return;
-  const long long t0 = clock64();
+  uint32_t probes = 0;
+  long long t0 = 0;
   while (!mbar_try_wait(bar, parity)) {
-    if (clock64() - t0 > 4000000000LL) {   // ~2 s: a protocol bug, not a slow tile
-      printf("mmpfn: mbarrier timeout (block %d,%d thread %d)\n", blockIdx.x, blockIdx.y, threadIdx.x);
-      __trap();
+    if ((++probes & 0x3FFFu) == 0) {
+      const long long now = clock64();
+      if (t0 == 0) t0 = now;
+      else if (now - t0 > 4000000000LL) mbar_timeout();   // ~2 s: a protocol bug, not a slow tile
     }
   }
 }
@@ -190,19 +198,21 @@ __global__ void __launch_bounds__(G_THREADS) tc_gemm_kernel(const __grid_constan
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int KB = p.K / G_BK;
-  const int n0 = blockIdx.y * G_BN;
+  const int n_tiles = p.N / G_BN;
+  const int n0 = (blockIdx.x % n_tiles) * G_BN;
+  const int m_tile = blockIdx.x / n_tiles;
 
   // tile coordinates
   int m0 = 0, tb = 0, tt = 0, s0 = 0;
   if (p.items) {
-    const int mt = blockIdx.x;
+    const int mt = m_tile;
     const int per_b = p.T * p.tiles_s;
     tb = mt / per_b;
     const int r = mt % per_b;
     tt = r / p.tiles_s;
     s0 = (r % p.tiles_s) * G_BM;
   } else {
-    m0 = blockIdx.x * G_BM;
+    m0 = m_tile * G_BM;
   }
 
   if (threadIdx.x == 0) {
@@ -332,7 +342,7 @@ __global__ void __launch_bounds__(G_THREADS) tc_gemm_kernel(const __grid_constan
     } else {  // TC_EPI_QKV_ITEMS: n-tile j in {q,k,v}; 32-column chunk c = head
       const int s = s0 + r;
       const bool ok = s < p.S;
-      const int j = blockIdx.y;
+      const int j = blockIdx.x % n_tiles;
       const long long bt = (long long)tb * p.T + tt;
 #pragma unroll 1
       for (int h = 0; h < kH; ++h) {
@@ -448,14 +458,14 @@ int launch_tc_gemm(const TcGemm& p, cudaStream_t st) {
     const cuuint64_t strides[3] = {(cuuint64_t)p.K * 2, (cuuint64_t)p.T * p.K * 2, (cuuint64_t)p.S * p.T * p.K * 2};
     const cuuint32_t box[4] = {G_BK, 1, G_BM, 1};
     MMPFN_TRY(encode_map(&ma, p.A, 4, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_128B));
-    grid = dim3((unsigned)(p.B * p.T * a.tiles_s), p.N / G_BN);
+    grid = dim3((unsigned)(p.B * p.T * a.tiles_s) * (p.N / G_BN));
   } else {
     if (p.M <= 0) return MMPFN_OK;
     const cuuint64_t dims[2] = {(cuuint64_t)p.K, (cuuint64_t)p.M};
     const cuuint64_t strides[1] = {(cuuint64_t)p.K * 2};
     const cuuint32_t box[2] = {G_BK, G_BM};
     MMPFN_TRY(encode_map(&ma, p.A, 2, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_128B));
-    grid = dim3((unsigned)((p.M + G_BM - 1) / G_BM), p.N / G_BN);
+    grid = dim3((unsigned)((p.M + G_BM - 1) / G_BM) * (p.N / G_BN));
   }
   {
     const cuuint64_t dims[2] = {(cuuint64_t)p.K, (cuuint64_t)p.N};
@@ -493,10 +503,10 @@ constexpr int A_THREADS = 192;
 
 struct AttnArgs {
   uint16_t* out;
-  int T, n_q, n_kv, shared_kv;
+  int T, n_q, n_kv, shared_kv, q_tiles;
 };
 
-__global__ void __launch_bounds__(A_THREADS) tc_item_attn_kernel(const __grid_constant__ CUtensorMap map_q,
+__global__ void __launch_bounds__(A_THREADS, 2) tc_item_attn_kernel(const __grid_constant__ CUtensorMap map_q,
                                                                  const __grid_constant__ CUtensorMap map_k,
                                                                  const __grid_constant__ CUtensorMap map_vt,
                                                                  const AttnArgs p) {
@@ -509,11 +519,12 @@ __global__ void __launch_bounds__(A_THREADS) tc_item_attn_kernel(const __grid_co
   uint64_t* s_full = bars + 5;
   uint64_t* p_full = bars + 6;
   uint64_t* pv_done = bars + 7;
-  uint32_t* tmem_slot = (uint32_t*)(bars + 8);
+  uint64_t* s_free = bars + 8;
+  uint32_t* tmem_slot = (uint32_t*)(bars + 9);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int plane = blockIdx.x;                 // (b*T + t)*kH + h
-  const int q0 = blockIdx.y * A_BQ;
+  const int plane = blockIdx.x / p.q_tiles;     // (b*T + t)*kH + h; q tiles of a plane are adjacent CTAs
+  const int q0 = (blockIdx.x % p.q_tiles) * A_BQ;
   const int h = plane % kH;
   const int bt = plane / kH;
   const int kv_plane = p.shared_kv ? bt : plane;
@@ -531,6 +542,7 @@ __global__ void __launch_bounds__(A_THREADS) tc_item_attn_kernel(const __grid_co
     mbar_init(s_full, 1);
     mbar_init(p_full, 128);
     mbar_init(pv_done, 1);
+    mbar_init(s_free, 128);
     fence_barrier_init();
   }
   if (warp == 1) tmem_alloc(tmem_slot, A_TMEM_COLS);
@@ -574,9 +586,11 @@ __global__ void __launch_bounds__(A_THREADS) tc_item_attn_kernel(const __grid_co
       issue_s(0);
       for (int j = 0; j < nkt; ++j) {
         const int s = j % A_KV_STAGES;
-        mbar_wait(p_full, j & 1);              // P(j) is in shared memory, S(j) has been read out of TMEM
+        mbar_wait(s_free, j & 1);              // S(j) is in the softmax registers: its columns are free
         tc_fence_after();
-        if (j + 1 < nkt) issue_s(j + 1);
+        if (j + 1 < nkt) issue_s(j + 1);       // S(j+1) runs under the softmax math of tile j
+        mbar_wait(p_full, j & 1);              // P(j) is in shared memory
+        tc_fence_after();
 #pragma unroll
         for (int k = 0; k < A_BK / 16; ++k) {
           const uint64_t pdesc = make_desc(sbase + A_OFF_P + (k / 4) * (A_P_BYTES / 2) + (k % 4) * 32, 1024, kSw128);
@@ -597,26 +611,33 @@ __global__ void __launch_bounds__(A_THREADS) tc_item_attn_kernel(const __grid_co
     uint8_t* prow = smem + A_OFF_P + r * 128;
     const int rsw = r & 7;
     float m_run = -INFINITY, l_run = 0.f;
-    uint32_t v[32];
+    uint32_t s0[32], s1[32], s2[32], s3[32];
     for (int j = 0; j < nkt; ++j) {
       mbar_wait(s_full, j & 1);
       tc_fence_after();
+      // the whole 128-key row of S into registers, then hand the S columns back to the MMA warp
+      tmem_ld32(tmem_s + lane_off + 0, s0);
+      tmem_ld32(tmem_s + lane_off + 32, s1);
+      tmem_ld32(tmem_s + lane_off + 64, s2);
+      tmem_ld32(tmem_s + lane_off + 96, s3);
+      tmem_ld_wait();
+      tc_fence_before();
+      mbar_arrive(s_free);
       const int valid = p.n_kv - j * A_BK;       // keys of this tile that exist
-      // pass 1: row maximum
-      float mx = -INFINITY;
-#pragma unroll 1
-      for (int cc = 0; cc < 4; ++cc) {
-        tmem_ld32(tmem_s + lane_off + cc * 32, v);
-        tmem_ld_wait();
-        if (valid >= A_BK) {
+      if (valid < A_BK) {                        // last, partial tile only: mask the missing keys
 #pragma unroll
-          for (int i = 0; i < 32; ++i) mx = fmaxf(mx, __uint_as_float(v[i]));
-        } else {
-#pragma unroll
-          for (int i = 0; i < 32; ++i)
-            if (cc * 32 + i < valid) mx = fmaxf(mx, __uint_as_float(v[i]));
+        for (int i = 0; i < 32; ++i) {
+          if (i >= valid) s0[i] = 0xff800000u;
+          if (32 + i >= valid) s1[i] = 0xff800000u;
+          if (64 + i >= valid) s2[i] = 0xff800000u;
+          if (96 + i >= valid) s3[i] = 0xff800000u;
         }
       }
+      float mx = -INFINITY;
+#pragma unroll
+      for (int i = 0; i < 32; ++i)
+        mx = fmaxf(fmaxf(mx, fmaxf(__uint_as_float(s0[i]), __uint_as_float(s1[i]))),
+                   fmaxf(__uint_as_float(s2[i]), __uint_as_float(s3[i])));
       const float m_new = fmaxf(m_run, mx);
       const float alpha = fast_exp2((m_run - m_new) * c);
       const float mc = m_new * c;
@@ -625,25 +646,18 @@ __global__ void __launch_bounds__(A_THREADS) tc_item_attn_kernel(const __grid_co
         mbar_wait(pv_done, (j - 1) & 1);
         tc_fence_after();
       }
-      // pass 2: p = exp2(s*c - m*c), bf16 into the 128B-swizzled A tile of the PV MMA
+      // p = exp2(s*c - m*c) as bf16 into the 128B-swizzled A tile of the PV MMA: 32 keys = 4 chunks
+      // of 16 B inside k-block (cc / 2); chunk index XOR (row & 7)
       float lsum = 0.f;
-#pragma unroll 1
-      for (int cc = 0; cc < 4; ++cc) {
-        tmem_ld32(tmem_s + lane_off + cc * 32, v);
-        tmem_ld_wait();
+      auto emit = [&](const uint32_t (&v)[32], int cc) {
         uint32_t pk[16];
 #pragma unroll
         for (int i = 0; i < 16; ++i) {
-          float a = fast_exp2(fmaf(__uint_as_float(v[2 * i]), c, -mc));
-          float b = fast_exp2(fmaf(__uint_as_float(v[2 * i + 1]), c, -mc));
-          if (valid < A_BK) {
-            if (cc * 32 + 2 * i >= valid) a = 0.f;
-            if (cc * 32 + 2 * i + 1 >= valid) b = 0.f;
-          }
+          const float a = fast_exp2(fmaf(__uint_as_float(v[2 * i]), c, -mc));
+          const float b = fast_exp2(fmaf(__uint_as_float(v[2 * i + 1]), c, -mc));
           lsum += a + b;
           pk[i] = pack_bf16x2(a, b);
         }
-        // 32 keys = 4 chunks of 16 B inside k-block (cc / 2); chunk index XOR (row & 7)
         uint8_t* kb = prow + (cc >> 1) * (A_P_BYTES / 2);
 #pragma unroll
         for (int q = 0; q < 4; ++q) {
@@ -651,22 +665,27 @@ __global__ void __launch_bounds__(A_THREADS) tc_item_attn_kernel(const __grid_co
           *reinterpret_cast<uint4*>(kb + ((chunk ^ rsw) << 4)) =
               make_uint4(pk[4 * q], pk[4 * q + 1], pk[4 * q + 2], pk[4 * q + 3]);
         }
-      }
+      };
+      emit(s0, 0);
+      emit(s1, 1);
+      emit(s2, 2);
+      emit(s3, 3);
       l_run = l_run * alpha + lsum;
       m_run = m_new;
       // rescale the running output when some row of this warp moved its maximum
       if (j > 0 && __any_sync(0xffffffffu, alpha != 1.0f)) {
-        tmem_ld32(tmem_o + lane_off, v);
+        tmem_ld32(tmem_o + lane_off, s0);
         tmem_ld_wait();
 #pragma unroll
-        for (int i = 0; i < 32; ++i) v[i] = __float_as_uint(__uint_as_float(v[i]) * alpha);
-        tmem_st32(tmem_o + lane_off, v);
+        for (int i = 0; i < 32; ++i) s0[i] = __float_as_uint(__uint_as_float(s0[i]) * alpha);
+        tmem_st32(tmem_o + lane_off, s0);
         tmem_st_wait();
       }
       fence_proxy_async();
       tc_fence_before();
       mbar_arrive(p_full);
     }
+    uint32_t (&v)[32] = s0;
     mbar_wait(pv_done, (nkt - 1) & 1);
     tc_fence_after();
     tmem_ld32(tmem_o + lane_off, v);
@@ -700,7 +719,7 @@ int launch_tc_item_attn(const TcItemAttn& p, cudaStream_t st) {
   const long long planes_q = (long long)p.B * p.T * kH;
   const long long planes_kv = p.shared_kv ? (long long)p.B * p.T : planes_q;
   const int q_tiles = (p.n_q + A_BQ - 1) / A_BQ;
-  if (q_tiles > 65535) { set_error("item attention: %d query tiles exceed grid.y", q_tiles); return MMPFN_EUNSUPPORTED; }
+  if (planes_q * q_tiles > 2147483647LL) { set_error("item attention: grid too large"); return MMPFN_EUNSUPPORTED; }
   CUtensorMap mq, mk, mvt;
   {
     const cuuint64_t dims[3] = {(cuuint64_t)kD, (cuuint64_t)p.n_q, (cuuint64_t)planes_q};
@@ -725,8 +744,8 @@ int launch_tc_item_attn(const TcItemAttn& p, cudaStream_t st) {
     cudaFuncSetAttribute(tc_item_attn_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, A_SMEM);
     configured = true;
   }
-  AttnArgs a{p.out, p.T, p.n_q, p.n_kv, p.shared_kv};
-  tc_item_attn_kernel<<<dim3((unsigned)planes_q, q_tiles), A_THREADS, A_SMEM, st>>>(mq, mk, mvt, a);
+  AttnArgs a{p.out, p.T, p.n_q, p.n_kv, p.shared_kv, q_tiles};
+  tc_item_attn_kernel<<<dim3((unsigned)(planes_q * q_tiles)), A_THREADS, A_SMEM, st>>>(mq, mk, mvt, a);
   return count_launch();
 }
 

@@ -86,6 +86,7 @@ class ShardedEngine:
         from .model import TrainContext
         eng, m = self.engine, self.model
         dev = m.device
+        eng.nan_flag.zero_()
         img_test_dev = staged["img_test"]
         tok = None
         n_img_train = 0
@@ -105,8 +106,11 @@ class ShardedEngine:
             ytr = g["y_train"][sub.pos].contiguous()
             n_tr = ytr.shape[1]
             X_full = None if Xte is None else torch.cat([Xtr, Xte], dim=1)
+            ls = g["label_stats"]
             mine[si] = m.fit_context(Xtr, None, ytr, X_all=X_full,
-                                     img_tok_train=None if tok is None else tok[:n_tr], check=False)
+                                     img_tok_train=None if tok is None else tok[:n_tr], check=False,
+                                     label_stats=(ls[0][sub.pos].contiguous(), ls[1][sub.pos].contiguous()),
+                                     nan_flag=eng.nan_flag)
         # 2. replicate every context (the exchange step)
         ctxs: Dict[int, TrainContext] = {}
         for si, sub in enumerate(self.subs):
@@ -133,10 +137,15 @@ class ShardedEngine:
         for si, sub in enumerate(self.subs):
             Xte = staged["X_test"][sub.group]
             Xte = None if Xte is None else Xte[sub.pos].contiguous()
-            lg = m.predict_with_context(ctxs[si], Xte, None, img_tok_test=tok_test)
+            lg = m.predict_with_context(ctxs[si], Xte, None, img_tok_test=tok_test, check=False,
+                                        nan_flag=eng.nan_flag)
             for k, i in enumerate(sub.members):
                 out[i] = lg[k]
         return torch.stack(out)
 
-    def logits(self, X_test_per_member, image_test) -> torch.Tensor:
+    def logits(self, X_test_per_member, image_test, *, graph: bool = False) -> torch.Tensor:
+        # collectives inside: replayed eagerly (NCCL graph capture is left for a later round)
         return self.logits_staged(self.stage(X_test_per_member, image_test))
+
+    def check_nan(self):
+        self.engine.check_nan()

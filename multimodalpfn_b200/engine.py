@@ -85,9 +85,14 @@ class B200InferenceEngine:
                                                  for i in idx])).to(dev)
             ytr = torch.from_numpy(np.stack([np.asarray(self.members[i]["y_train"], dtype=np.float32)
                                              for i in idx])).to(dev)
-            self.groups.append(dict(F=F, idx=idx, X_train=Xtr, y_train=ytr, ctx=None))
+            # label statistics need a host sync (unique labels): once here, not per call
+            self.groups.append(dict(F=F, idx=idx, X_train=Xtr, y_train=ytr, ctx=None,
+                                    label_stats=type(model).label_stats(ytr)))
         self.img_train_dev = None if self.image_train is None else torch.from_numpy(self.image_train).to(dev)
         self._img_tok_train = None
+        self.nan_flag = torch.zeros(1, dtype=torch.int32, device=dev)
+        self._graphs = {}
+        self.launches_per_call = None
         if cache_context:
             self._build_contexts()
 
@@ -95,7 +100,8 @@ class B200InferenceEngine:
         if self.img_train_dev is not None and self._img_tok_train is None:
             self._img_tok_train = self.model.stem_image(self.img_train_dev)
         for g in self.groups:
-            g["ctx"] = self.model.fit_context(g["X_train"], None, g["y_train"], img_tok_train=self._img_tok_train)
+            g["ctx"] = self.model.fit_context(g["X_train"], None, g["y_train"], img_tok_train=self._img_tok_train,
+                                              label_stats=g["label_stats"])
             if self.img_train_dev is not None:
                 g["ctx"].n_tok = self.img_train_dev.shape[1]
 
@@ -123,10 +129,12 @@ class B200InferenceEngine:
         m = self.model
         out = [None] * len(self.members)
         img_test_dev = staged["img_test"]
+        flag = self.nan_flag
+        flag.zero_()
         if self.cache_context:
             tok_test = m.stem_image(img_test_dev) if img_test_dev is not None else None
             for g, Xte in zip(self.groups, staged["X_test"]):
-                lg = m.predict_with_context(g["ctx"], Xte, None, img_tok_test=tok_test)
+                lg = m.predict_with_context(g["ctx"], Xte, None, img_tok_test=tok_test, check=False, nan_flag=flag)
                 for k, i in enumerate(g["idx"]):
                     out[i] = lg[k]
         else:
@@ -138,11 +146,54 @@ class B200InferenceEngine:
                 n_tr = g["y_train"].shape[1]
                 X_full = None if Xte is None else torch.cat([g["X_train"], Xte], dim=1)
                 ctx = m.fit_context(g["X_train"], None, g["y_train"], X_all=X_full,
-                                    img_tok_train=None if tok is None else tok[:n_tr], check=False)
-                lg = m.predict_with_context(ctx, Xte, None, img_tok_test=None if tok is None else tok[n_tr:])
+                                    img_tok_train=None if tok is None else tok[:n_tr], check=False,
+                                    label_stats=g["label_stats"], nan_flag=flag)
+                lg = m.predict_with_context(ctx, Xte, None, img_tok_test=None if tok is None else tok[n_tr:],
+                                            check=False, nan_flag=flag)
                 for k, i in enumerate(g["idx"]):
                     out[i] = lg[k]
         return torch.stack(out)
 
-    def logits(self, X_test_per_member: Sequence[Optional[np.ndarray]], image_test: Optional[np.ndarray]) -> torch.Tensor:
-        return self.logits_staged(self.stage(X_test_per_member, image_test))
+    def check_nan(self):
+        """One host sync: raises like the reference does when the stem produced NaN."""
+        self.model._check_nan(self.nan_flag)
+
+    # ---- CUDA-graph replay of the device-resident step ------------------------------------------
+    def logits_graphed(self, staged) -> torch.Tensor:
+        """Replays ``logits_staged`` as one CUDA graph (launch-latency bound otherwise: ~400 kernels
+        per call).  ``staged`` is copied into static input buffers; the returned tensor is the
+        graph's static output (valid until the next call)."""
+        key = (tuple(None if x is None else tuple(x.shape) for x in staged["X_test"]),
+               None if staged["img_test"] is None else tuple(staged["img_test"].shape))
+        ent = self._graphs.get(key)
+        if ent is None:
+            static = dict(X_test=[None if x is None else x.clone() for x in staged["X_test"]],
+                          img_test=None if staged["img_test"] is None else staged["img_test"].clone())
+            side = torch.cuda.Stream(device=self.model.device)
+            side.wait_stream(torch.cuda.current_stream(self.model.device))
+            with torch.cuda.stream(side):
+                for _ in range(2):                     # warm-up: sizes every scratch buffer, fills caches
+                    self.logits_staged(static)
+            torch.cuda.current_stream(self.model.device).wait_stream(side)
+            torch.cuda.synchronize(self.model.device)
+            graph = torch.cuda.CUDAGraph()
+            l0 = _lib.launch_count()
+            with torch.cuda.graph(graph):
+                out = self.logits_staged(static)
+            self.launches_per_call = _lib.launch_count() - l0
+            ent = (graph, static, out)
+            self._graphs[key] = ent
+        graph, static, out = ent
+        for dst, src in zip(static["X_test"], staged["X_test"]):
+            if dst is not None:
+                dst.copy_(src, non_blocking=True)
+        if static["img_test"] is not None:
+            static["img_test"].copy_(staged["img_test"], non_blocking=True)
+        graph.replay()
+        return out
+
+    def logits(self, X_test_per_member: Sequence[Optional[np.ndarray]], image_test: Optional[np.ndarray], *,
+               graph: bool = True) -> torch.Tensor:
+        staged = self.stage(X_test_per_member, image_test)
+        out = self.logits_graphed(staged) if graph else self.logits_staged(staged)
+        return out

@@ -238,7 +238,8 @@ class B200PerFeatureTransformer:
             raise ValueError("There should be no NaNs in the encoded x and y. Check that you do not feed NaNs "
                              "or use a NaN-handling encoder (an all-NaN column or inf in a train column).")
 
-    def fit_context(self, X_train, img_train, y_train, *, X_all=None, img_tok_train=None, check=True) -> TrainContext:
+    def fit_context(self, X_train, img_train, y_train, *, X_all=None, img_tok_train=None, check=True,
+                    label_stats=None, nan_flag=None) -> TrainContext:
         """Run the train rows through the stem and the 12 layers once; keep the K/V context.
 
         X_train [B, Ntr, F] (or [Ntr, F]) / img_train [Ntr, n_tok, img_dim] / y_train [B, Ntr].
@@ -265,12 +266,13 @@ class B200PerFeatureTransformer:
                     stats = self.stem_tab_fit(X_train, n_train)
             if img_tok_train is None and img_train is not None:
                 img_tok_train = self.stem_image(img_train)
-            y_mean, y_mask = self.label_stats(y_train)
+            # label statistics involve a host sync: callers that replay a CUDA graph pass them in
+            y_mean, y_mask = label_stats if label_stats is not None else self.label_stats(y_train)
             G = self._n_groups(F) if X_train is not None else 0
             H_img = 0 if img_tok_train is None else img_tok_train.shape[1]
             T = G + H_img + 1
             pos = self.positional_embeddings(T - 1)
-            flag = torch.zeros(1, dtype=torch.int32, device=self.device)
+            flag = nan_flag if nan_flag is not None else torch.zeros(1, dtype=torch.int32, device=self.device)
             state, state_b = self.embed(X_train, stats, img_tok_train, y_train, y_mean, y_mask, pos, B=B, S=n_train,
                                         F=F, x_bstride=n_train * F, y_bstride=n_train, nan_flag=flag)
             kv = self.alloc_kv(B, n_train, T)
@@ -280,7 +282,8 @@ class B200PerFeatureTransformer:
             return TrainContext(B=B, n_train=n_train, F=F, T=T, n_tok=n_tok, kv=kv, tab_stats=stats, y_mean=y_mean,
                                 y_mask=y_mask, pos_emb=pos, precision=self.precision)
 
-    def predict_with_context(self, ctx: TrainContext, X_test, img_test, *, img_tok_test=None, check=True):
+    def predict_with_context(self, ctx: TrainContext, X_test, img_test, *, img_tok_test=None, check=True,
+                             nan_flag=None):
         """Test rows only -> logits [B, Nte, n_out]."""
         with torch.cuda.device(self.device):
             X_test, img_test = self._prep(X_test, img_test)
@@ -290,7 +293,7 @@ class B200PerFeatureTransformer:
             if X_test is not None and (X_test.shape[0] != ctx.B or X_test.shape[2] != ctx.F):
                 raise ValueError(f"test table {tuple(X_test.shape)} does not match the context (B {ctx.B}, F {ctx.F})")
             y_nan = torch.full((1, n_test), float("nan"), dtype=torch.float32, device=self.device)
-            flag = torch.zeros(1, dtype=torch.int32, device=self.device)
+            flag = nan_flag if nan_flag is not None else torch.zeros(1, dtype=torch.int32, device=self.device)
             state, state_b = self.embed(X_test, ctx.tab_stats, img_tok_test, y_nan, ctx.y_mean, ctx.y_mask, ctx.pos_emb,
                                         B=ctx.B, S=n_test, F=ctx.F, x_bstride=n_test * ctx.F, y_bstride=0,
                                         nan_flag=flag)

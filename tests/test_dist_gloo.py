@@ -51,7 +51,15 @@ class FakeModel:
     def positional_embeddings(self, n):
         return torch.arange(n, dtype=torch.float32)
 
-    def fit_context(self, X_train, img, y_train, *, X_all=None, img_tok_train=None, check=True):
+    @staticmethod
+    def label_stats(y):
+        return y.mean(1), y.sum(1).to(torch.int64)
+
+    def _check_nan(self, flag):
+        assert int(flag.item()) == 0
+
+    def fit_context(self, X_train, img, y_train, *, X_all=None, img_tok_train=None, check=True, label_stats=None,
+                    nan_flag=None):
         B, n_tr, F = X_train.shape
         G = self._n_groups(F)
         T = G + img_tok_train.shape[1] + 1
@@ -63,7 +71,7 @@ class FakeModel:
                             y_mean=y_train.mean(1), y_mask=y_train.sum(1).to(torch.int64),
                             pos_emb=self.positional_embeddings(T - 1), precision=1)
 
-    def predict_with_context(self, ctx, X_test, img, *, img_tok_test=None, check=True):
+    def predict_with_context(self, ctx, X_test, img, *, img_tok_test=None, check=True, nan_flag=None):
         B, n_te, F = X_test.shape
         sig = ctx.kv.view(torch.float64).view(B, ctx.T).sum(1).to(torch.float32)
         base = X_test.sum(2) + img_tok_test.sum((1, 2))[None] + ctx.tab_stats.sum(1)[:, None] + ctx.y_mean[:, None]
@@ -92,7 +100,7 @@ def _worker(rank, world, port, q):
     dist.init_process_group("gloo", rank=rank, world_size=world)
     try:
         eng, X_tests, img_test = _make_engine(rank)
-        ref = eng.logits(X_tests, img_test)                       # unsharded, this rank's chunk
+        ref = eng.logits(X_tests, img_test, graph=False)          # unsharded, this rank's chunk
         sh = ShardedEngine(eng, rank, world)
         got = sh.logits(X_tests, img_test)
         ok = bool(torch.allclose(got, ref, rtol=0, atol=1e-5))
