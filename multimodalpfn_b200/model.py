@@ -80,6 +80,8 @@ class B200PerFeatureTransformer:
         self.ninp = geom.emsize
         self.features_per_group = geom.features_per_group
         self.cache_trainset_representation = False
+        # model/memory.py:185-189 counts len(model.transformer_encoder.layers)
+        self.transformer_encoder = type("LayerStackShim", (), {"layers": [None] * geom.nlayers})()
 
     # ------------------------------------------------------------------ nn.Module duck-typing
     def to(self, *a, **k):
