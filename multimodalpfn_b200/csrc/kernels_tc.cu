@@ -37,10 +37,10 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
   uint32_t ok;
   asm volatile(
       "{\n\t.reg .pred p;\n\t"
-      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
       "selp.u32 %0, 1, 0, p;\n\t}"
       : "=r"(ok)
-      : "r"(smem_u32(bar)), "r"(parity)
+      : "r"(smem_u32(bar)), "r"(parity), "r"(20000u)   // suspend-time hint (ns): sleep in hardware, not in a spin
       : "memory");
   return ok != 0;
 }
@@ -496,7 +496,8 @@ constexpr int A_KV_STAGES = 2;
 constexpr int A_OFF_K = A_Q_BYTES;
 constexpr int A_OFF_VT = A_OFF_K + A_KV_STAGES * A_K_BYTES;
 constexpr int A_OFF_P = A_OFF_VT + A_KV_STAGES * A_VT_BYTES;
-constexpr int A_OFF_BAR = A_OFF_P + A_P_BYTES;
+constexpr int A_P_STAGES = 2;
+constexpr int A_OFF_BAR = A_OFF_P + A_P_STAGES * A_P_BYTES;
 constexpr int A_SMEM = A_OFF_BAR + 256 + 1024;
 constexpr int A_TMEM_COLS = 256;                  // S: [0,128)  O: [128,160)
 constexpr int A_THREADS = 192;
@@ -593,7 +594,8 @@ __global__ void __launch_bounds__(A_THREADS, 2) tc_item_attn_kernel(const __grid
         tc_fence_after();
 #pragma unroll
         for (int k = 0; k < A_BK / 16; ++k) {
-          const uint64_t pdesc = make_desc(sbase + A_OFF_P + (k / 4) * (A_P_BYTES / 2) + (k % 4) * 32, 1024, kSw128);
+          const uint64_t pdesc =
+              make_desc(sbase + A_OFF_P + (j & 1) * A_P_BYTES + (k / 4) * (A_P_BYTES / 2) + (k % 4) * 32, 1024, kSw128);
           const uint64_t vdesc =
               make_desc(sbase + A_OFF_VT + s * A_VT_BYTES + (k / 4) * (A_VT_BYTES / 2) + (k % 4) * 32, 1024, kSw128);
           umma_bf16(tmem_o, pdesc, vdesc, idesc_o, (j | k) != 0);
@@ -641,11 +643,8 @@ __global__ void __launch_bounds__(A_THREADS, 2) tc_item_attn_kernel(const __grid
       const float m_new = fmaxf(m_run, mx);
       const float alpha = fast_exp2((m_run - m_new) * c);
       const float mc = m_new * c;
-      // P(j-1) must have been consumed by its MMA before P is overwritten / O is rescaled
-      if (j > 0) {
-        mbar_wait(pv_done, (j - 1) & 1);
-        tc_fence_after();
-      }
+      // P is double buffered: buffer (j & 1) was last read by PV(j-2), which the wait at the end of
+      // tile j-1 has already covered.
       // p = exp2(s*c - m*c) as bf16 into the 128B-swizzled A tile of the PV MMA: 32 keys = 4 chunks
       // of 16 B inside k-block (cc / 2); chunk index XOR (row & 7)
       float lsum = 0.f;
@@ -658,7 +657,7 @@ __global__ void __launch_bounds__(A_THREADS, 2) tc_item_attn_kernel(const __grid
           lsum += a + b;
           pk[i] = pack_bf16x2(a, b);
         }
-        uint8_t* kb = prow + (cc >> 1) * (A_P_BYTES / 2);
+        uint8_t* kb = prow + (j & 1) * A_P_BYTES + (cc >> 1) * (A_P_BYTES / 2);
 #pragma unroll
         for (int q = 0; q < 4; ++q) {
           const int chunk = (cc & 1) * 4 + q;
@@ -672,6 +671,11 @@ __global__ void __launch_bounds__(A_THREADS, 2) tc_item_attn_kernel(const __grid
       emit(s3, 3);
       l_run = l_run * alpha + lsum;
       m_run = m_new;
+      // PV(j-1) must be complete before O is rescaled here and before PV(j) may be issued
+      if (j > 0) {
+        mbar_wait(pv_done, (j - 1) & 1);
+        tc_fence_after();
+      }
       // rescale the running output when some row of this warp moved its maximum
       if (j > 0 && __any_sync(0xffffffffu, alpha != 1.0f)) {
         tmem_ld32(tmem_o + lane_off, s0);
