@@ -13,6 +13,7 @@
 // Every mbarrier wait is bounded (trap after ~2 s) so that a protocol bug cannot hang the GPU.
 #include <cuda.h>
 #include <stdio.h>
+#include <stdlib.h>
 
 #include "common.cuh"
 
@@ -33,33 +34,39 @@ __device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
 __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
-__device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
-  uint32_t ok;
-  asm volatile(
-      "{\n\t.reg .pred p;\n\t"
-      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
-      "selp.u32 %0, 1, 0, p;\n\t}"
-      : "=r"(ok)
-      : "r"(smem_u32(bar)), "r"(parity), "r"(20000u)   // suspend-time hint (ns): sleep in hardware, not in a spin
-      : "memory");
-  return ok != 0;
-}
 __device__ __noinline__ void mbar_timeout() {
   printf("mmpfn: mbarrier timeout (block %d,%d thread %d)\n", blockIdx.x, blockIdx.y, threadIdx.x);
   __trap();
 }
-// try_wait suspends the thread in hardware for a bounded time per call; the clock is only consulted
-// every 2^14 failed probes so that the spinning producer / MMA lanes do not eat issue slots.
+// try_wait suspends the thread in hardware for a bounded time per probe (the 20 us hint), so the poll
+// loop is three instructions; the clock is consulted once every 2^12 failed probes and a wait that
+// lasts ~2 s traps (a protocol bug, not a slow tile) instead of hanging the GPU.
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
-  if (mbar_try_wait(bar, parity)) return;
-  uint32_t probes = 0;
+  const uint32_t addr = smem_u32(bar);
   long long t0 = 0;
-  while (!mbar_try_wait(bar, parity)) {
-    if ((++probes & 0x3FFFu) == 0) {
-      const long long now = clock64();
-      if (t0 == 0) t0 = now;
-      else if (now - t0 > 4000000000LL) mbar_timeout();   // ~2 s: a protocol bug, not a slow tile
-    }
+  while (true) {
+    uint32_t done;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t.reg .u32 n;\n\t"
+        "mov.u32 n, 0;\n\t"
+        "WAIT_%=:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
+        "@p bra DONE_%=;\n\t"
+        "add.u32 n, n, 1;\n\t"
+        "setp.lt.u32 p, n, 4096;\n\t"
+        "@p bra WAIT_%=;\n\t"
+        "mov.u32 %0, 0;\n\t"
+        "bra EXIT_%=;\n\t"
+        "DONE_%=:\n\t"
+        "mov.u32 %0, 1;\n\t"
+        "EXIT_%=:\n\t}"
+        : "=r"(done)
+        : "r"(addr), "r"(parity), "r"(20000u)
+        : "memory");
+    if (done) return;
+    const long long now = clock64();
+    if (t0 == 0) t0 = now;
+    else if (now - t0 > 4000000000LL) mbar_timeout();
   }
 }
 __device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
@@ -126,6 +133,15 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
       : "r"(taddr)
       : "memory");
 }
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&v)[16]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
+        "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15])
+      : "r"(taddr)
+      : "memory");
+}
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 __device__ __forceinline__ void tmem_st32(uint32_t taddr, const uint32_t (&v)[32]) {
   asm volatile(
@@ -144,6 +160,45 @@ __device__ __forceinline__ float fast_exp2(float x) {
   float y;
   asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
   return y;
+}
+
+// 2^x on the FMA/ALU pipes (no MUFU): x = n + f with n = round(x), f in [-0.5, 0.5]; 2^f by a
+// degree-3 minimax polynomial (max relative error 7.6e-5, far below the bf16 rounding of P), the
+// integer part spliced into the exponent field.  x is clamped at -126 (result ~1e-38 ~ 0).
+__device__ __forceinline__ float poly_exp2(float x) {
+  x = fmaxf(x, -126.0f);
+  const float r = x + 12582912.0f;            // 1.5 * 2^23: round(x) lands in the low mantissa bits
+  const float f = x - (r - 12582912.0f);
+  float p = fmaf(0.05520550534129143f, f, 0.24261397123336792f);
+  p = fmaf(p, f, 0.6932547688484192f);
+  p = fmaf(p, f, 0.9999276995658875f);
+  return __uint_as_float(__float_as_uint(p) + (__float_as_uint(r) << 23));
+}
+// which of the 32 elements of a register chunk take the polynomial: PN of 32, evenly spread
+__host__ __device__ constexpr bool poly_sel(int i, int PN) { return ((i + 1) * PN) / 32 != (i * PN) / 32; }
+
+// packed fp32 pairs (FFMA2 / FADD2): one issue slot for two lanes of the softmax arithmetic
+__device__ __forceinline__ uint64_t pack_f32x2(float lo, float hi) {
+  uint64_t r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+  return r;
+}
+__device__ __forceinline__ void unpack_f32x2(uint64_t v, float& lo, float& hi) {
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v));
+}
+__device__ __forceinline__ uint64_t fma_f32x2(uint64_t a, uint64_t b, uint64_t c) {
+  uint64_t r;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c));
+  return r;
+}
+__device__ __forceinline__ uint64_t add_f32x2(uint64_t a, uint64_t b) {
+  uint64_t r;
+  asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+  return r;
+}
+
+__device__ __forceinline__ void st_shared_v4(uint32_t saddr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
+  asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(saddr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
 }
 
 // UMMA shared-memory operand descriptor, K-major, swizzled (cute::UMMA::SmemDescriptor layout):
@@ -487,11 +542,21 @@ int launch_tc_gemm(const TcGemm& p, cudaStream_t st) {
 // Item attention
 // ---------------------------------------------------------------------------------------------
 namespace {
-constexpr int A_BQ = 128, A_BK = 128;
+// One CTA = one 128-query tile of one (b, t, head) plane; two CTAs per SM.  Key tiles hold 112 keys so
+// that TWO S accumulators (2 x 112 fp32 columns) and O (32) fit the 256 TMEM columns a CTA may take
+// with two CTAs per SM.  With S double buffered, S(j+2) is issued as soon as the softmax has pulled
+// S(j) into registers, a whole tile before it is needed: the mbarrier round trips (try_wait wake-up,
+// tcgen05.commit arrival: ~1900 cycles per tile measured with the math knocked out) leave the
+// softmax path, whose warps then run tile after tile without waiting.
+//   warps 0-3  softmax, thread = query row (TMEM lane quarter = warp)
+//   warp 4     TMA producer (K and V^T on separate rings) + TMEM allocation
+//   warp 5     MMA issue: S = Q K^T into TMEM, O += P V with P read from shared memory
+constexpr int A_BQ = 128, A_BK = 112;
 constexpr int A_Q_BYTES = A_BQ * kD * 2;          // 8 KB  (64B rows, 64B swizzle)
-constexpr int A_K_BYTES = A_BK * kD * 2;          // 8 KB
-constexpr int A_VT_BYTES = kD * A_BK * 2;         // 8 KB = 2 k-blocks x [32 rows][128 B], 128B swizzle
-constexpr int A_P_BYTES = A_BQ * A_BK * 2;        // 32 KB = 2 k-blocks x [128 rows][128 B], 128B swizzle
+constexpr int A_K_TX = A_BK * kD * 2;             // 7 KB per K tile
+constexpr int A_K_BYTES = 8192;                   // slot stride (1024-aligned)
+constexpr int A_VT_BYTES = 8192;                  // 2 k-blocks x [32 d][64 keys = 128 B], 128B swizzle (48 keys used in the 2nd)
+constexpr int A_P_BYTES = A_BQ * 128 * 2;         // 32 KB = 2 k-blocks x [128 rows][128 B], 128B swizzle
 constexpr int A_KV_STAGES = 2;
 constexpr int A_OFF_K = A_Q_BYTES;
 constexpr int A_OFF_VT = A_OFF_K + A_KV_STAGES * A_K_BYTES;
@@ -499,14 +564,23 @@ constexpr int A_OFF_P = A_OFF_VT + A_KV_STAGES * A_VT_BYTES;
 constexpr int A_P_STAGES = 2;
 constexpr int A_OFF_BAR = A_OFF_P + A_P_STAGES * A_P_BYTES;
 constexpr int A_SMEM = A_OFF_BAR + 256 + 1024;
-constexpr int A_TMEM_COLS = 256;                  // S: [0,128)  O: [128,160)
+constexpr int A_TMEM_COLS = 256;                  // S0: [0,112)  S1: [112,224)  O: [224,256)
 constexpr int A_THREADS = 192;
+constexpr int kAttnPolyDefault = 4;
 
 struct AttnArgs {
   uint16_t* out;
   int T, n_q, n_kv, shared_kv, q_tiles;
 };
 
+// DBG != 0: knock-out timing experiments (results are wrong): 1 no exp, 2 no S load from TMEM,
+// 4 no P store, 8 no P V MMA, 16 no S MMA, 32 no row maximum; 64 = clock64 trace of one CTA.
+__device__ long long g_attn_trace[4096];
+#define ATTN_TRACE(slot)                                                          \
+  do {                                                                            \
+    if ((DBG & 64) && blockIdx.x == 5001) g_attn_trace[(slot)] = clock64();       \
+  } while (0)
+template <int PN, int DBG = 0>
 __global__ void __launch_bounds__(A_THREADS, 2) tc_item_attn_kernel(const __grid_constant__ CUtensorMap map_q,
                                                                  const __grid_constant__ CUtensorMap map_k,
                                                                  const __grid_constant__ CUtensorMap map_vt,
@@ -515,13 +589,18 @@ __global__ void __launch_bounds__(A_THREADS, 2) tc_item_attn_kernel(const __grid
   uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
   uint64_t* bars = (uint64_t*)(smem + A_OFF_BAR);
   uint64_t* q_full = bars;
-  uint64_t* kv_full = bars + 1;        // [2]
-  uint64_t* kv_empty = bars + 3;       // [2]
-  uint64_t* s_full = bars + 5;
-  uint64_t* p_full = bars + 6;
-  uint64_t* pv_done = bars + 7;
-  uint64_t* s_free = bars + 8;
-  uint32_t* tmem_slot = (uint32_t*)(bars + 9);
+  uint64_t* k_full = bars + 1;         // [2]  K slot of tile j is free once S(j) has been computed,
+  uint64_t* k_empty = bars + 3;        // [2]  V^T slot once P V(j) has
+  uint64_t* v_full = bars + 5;         // [2]
+  uint64_t* v_empty = bars + 7;        // [2]
+  uint64_t* s_full = bars + 9;         // [2]  S(j) is in TMEM buffer j & 1
+  uint64_t* s_free = bars + 11;        // [2]  ... and has been pulled into the softmax registers
+  uint64_t* p_full = bars + 13;        // [2]  P(j) is in shared memory buffer j & 1.  Per buffer: a warp may run one
+                                       //      tile ahead of the slowest one, and its arrival must not count for it
+  uint64_t* pv_done = bars + 15;       // [2]  P V(j) has completed -> pv_done[j & 1].  The softmax only looks at it when
+                                       //      it has to (rescale, final read); with one barrier per parity of j a
+                                       //      parity wait stays unambiguous although phases go unobserved
+  uint32_t* tmem_slot = (uint32_t*)(bars + 17);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int plane = blockIdx.x / p.q_tiles;     // (b*T + t)*kH + h; q tiles of a plane are adjacent CTAs
@@ -536,95 +615,150 @@ __global__ void __launch_bounds__(A_THREADS, 2) tc_item_attn_kernel(const __grid
     prefetch_tmap(&map_k);
     prefetch_tmap(&map_vt);
     mbar_init(q_full, 1);
-    for (int s = 0; s < A_KV_STAGES; ++s) {
-      mbar_init(&kv_full[s], 1);
-      mbar_init(&kv_empty[s], 1);
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(&k_full[s], 1);
+      mbar_init(&k_empty[s], 1);
+      mbar_init(&v_full[s], 1);
+      mbar_init(&v_empty[s], 1);
+      mbar_init(&s_full[s], 1);
+      mbar_init(&s_free[s], 128);
+      mbar_init(&p_full[s], 128);
+      mbar_init(&pv_done[s], 1);
     }
-    mbar_init(s_full, 1);
-    mbar_init(p_full, 128);
-    mbar_init(pv_done, 1);
-    mbar_init(s_free, 128);
     fence_barrier_init();
   }
-  if (warp == 1) tmem_alloc(tmem_slot, A_TMEM_COLS);
+  if (warp == 4) tmem_alloc(tmem_slot, A_TMEM_COLS);
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem = *tmem_slot;
-  const uint32_t tmem_s = tmem, tmem_o = tmem + 128;
+  const uint32_t tmem_o = tmem + 2 * A_BK;
 
-  if (warp == 0) {
+  if (warp == 4) {
     if (lane == 0) {
       mbar_expect_tx(q_full, A_Q_BYTES);
       tma_load_3d(smem, &map_q, q_full, 0, q0, plane);
+      auto load_k = [&](int j) {
+        const int s = j & 1;
+        mbar_wait(&k_empty[s], ((j >> 1) & 1) ^ 1);
+        mbar_expect_tx(&k_full[s], A_K_TX);
+        tma_load_3d(smem + A_OFF_K + s * A_K_BYTES, &map_k, &k_full[s], 0, j * A_BK, kv_plane);
+      };
+      auto load_v = [&](int j) {
+        const int s = j & 1;
+        mbar_wait(&v_empty[s], ((j >> 1) & 1) ^ 1);
+        mbar_expect_tx(&v_full[s], A_VT_BYTES);
+        tma_load_3d(smem + A_OFF_VT + s * A_VT_BYTES, &map_vt, &v_full[s], j * A_BK, 0, kv_plane);
+        tma_load_3d(smem + A_OFF_VT + s * A_VT_BYTES + A_VT_BYTES / 2, &map_vt, &v_full[s], j * A_BK + 64, 0, kv_plane);
+      };
+      // issue order = the order in which the slots become free: S(j) is issued two tiles ahead of P V(j)
+      load_k(0);
+      if (nkt > 1) load_k(1);
       for (int j = 0; j < nkt; ++j) {
-        const int s = j % A_KV_STAGES;
-        mbar_wait(&kv_empty[s], ((j / A_KV_STAGES) & 1) ^ 1);
-        mbar_expect_tx(&kv_full[s], A_K_BYTES + A_VT_BYTES);
-        tma_load_3d(smem + A_OFF_K + s * A_K_BYTES, &map_k, &kv_full[s], 0, j * A_BK, kv_plane);
-        tma_load_3d(smem + A_OFF_VT + s * A_VT_BYTES, &map_vt, &kv_full[s], j * A_BK, 0, kv_plane);
-        tma_load_3d(smem + A_OFF_VT + s * A_VT_BYTES + A_VT_BYTES / 2, &map_vt, &kv_full[s], j * A_BK + 64, 0,
-                    kv_plane);
+        if (j + 2 < nkt) load_k(j + 2);
+        load_v(j);
       }
     }
-  } else if (warp == 1) {
+  } else if (warp == 5) {
     if (lane == 0) {
       constexpr uint32_t idesc_s = make_idesc(A_BQ, A_BK);
       constexpr uint32_t idesc_o = make_idesc(A_BQ, kD);
       const uint32_t sbase = smem_u32(smem);
       const uint64_t qdesc = make_desc(sbase, 512, kSw64);
+      // S(j) = Q K(j)^T into TMEM buffer j & 1; completion arrives on s_full and frees the K slot
       auto issue_s = [&](int j) {
-        const int s = j % A_KV_STAGES;
-        mbar_wait(&kv_full[s], (j / A_KV_STAGES) & 1);
-        tc_fence_after();
-        const uint64_t kdesc = make_desc(sbase + A_OFF_K + s * A_K_BYTES, 512, kSw64);
+        const int s = j & 1;
+        if (!(DBG & 16)) {
+          const uint64_t kdesc = make_desc(sbase + A_OFF_K + s * A_K_BYTES, 512, kSw64);
 #pragma unroll
-        for (int k = 0; k < kD / 16; ++k)
-          umma_bf16(tmem_s, qdesc + (uint64_t)(k * 2), kdesc + (uint64_t)(k * 2), idesc_s, k != 0);
-        umma_commit(s_full);
+          for (int k = 0; k < kD / 16; ++k)
+            umma_bf16(tmem + s * A_BK, qdesc + (uint64_t)(k * 2), kdesc + (uint64_t)(k * 2), idesc_s, k != 0);
+        }
+        umma_commit(&k_empty[s]);
       };
       mbar_wait(q_full, 0);
+      mbar_wait(&k_full[0], 0);
+      tc_fence_after();
       issue_s(0);
+      umma_commit(&s_full[0]);
+      if (nkt > 1) {
+        mbar_wait(&k_full[1], 0);
+        tc_fence_after();
+        issue_s(1);
+        umma_commit(&s_full[1]);
+      }
       for (int j = 0; j < nkt; ++j) {
-        const int s = j % A_KV_STAGES;
-        mbar_wait(s_free, j & 1);              // S(j) is in the softmax registers: its columns are free
-        tc_fence_after();
-        if (j + 1 < nkt) issue_s(j + 1);       // S(j+1) runs under the softmax math of tile j
-        mbar_wait(p_full, j & 1);              // P(j) is in shared memory
-        tc_fence_after();
-#pragma unroll
-        for (int k = 0; k < A_BK / 16; ++k) {
-          const uint64_t pdesc =
-              make_desc(sbase + A_OFF_P + (j & 1) * A_P_BYTES + (k / 4) * (A_P_BYTES / 2) + (k % 4) * 32, 1024, kSw128);
-          const uint64_t vdesc =
-              make_desc(sbase + A_OFF_VT + s * A_VT_BYTES + (k / 4) * (A_VT_BYTES / 2) + (k % 4) * 32, 1024, kSw128);
-          umma_bf16(tmem_o, pdesc, vdesc, idesc_o, (j | k) != 0);
+        const int s = j & 1;
+        const uint32_t ph = (j >> 1) & 1;
+        if (j + 2 < nkt) {
+          // the TMA wait first: it is long satisfied and must not sit behind the softmax hand-off
+          mbar_wait(&k_full[s], ph ^ 1);         // K(j+2): completion (j+2)/2 of slot s
+          mbar_wait(&s_free[s], ph);             // S(j) is in the softmax registers: its columns are free
+          tc_fence_after();
+          ATTN_TRACE(2048 + j * 4 + 0);
+          issue_s(j + 2);
+          ATTN_TRACE(2048 + j * 4 + 1);
         }
-        umma_commit(&kv_empty[s]);
-        umma_commit(pv_done);
+        mbar_wait(&v_full[s], ph);
+        mbar_wait(&p_full[s], ph);               // P(j) is in shared memory
+        tc_fence_after();
+        ATTN_TRACE(2048 + j * 4 + 2);
+        if (!(DBG & 8)) {
+          const uint64_t pdesc = make_desc(sbase + A_OFF_P + s * A_P_BYTES, 1024, kSw128);
+          const uint64_t vdesc = make_desc(sbase + A_OFF_VT + s * A_VT_BYTES, 1024, kSw128);
+#pragma unroll
+          for (int k = 0; k < A_BK / 16; ++k)
+            umma_bf16(tmem_o, pdesc + (uint64_t)((k / 4) * (A_P_BYTES >> 5) + (k % 4) * 2),
+                      vdesc + (uint64_t)((k / 4) * (A_VT_BYTES >> 5) + (k % 4) * 2), idesc_o, (j | k) != 0);
+        }
+        // ONE arrival tells the softmax both that S(j+2) is in TMEM buffer s and that P V(j) has
+        // released P buffer s (tcgen05 ops complete in issue order), so its loop waits once per tile
+        if (j + 2 < nkt) umma_commit(&s_full[s]);
+        umma_commit(&v_empty[s]);
+        umma_commit(&pv_done[s]);
+        ATTN_TRACE(2048 + j * 4 + 3);
       }
     }
   } else {
     // ---- softmax warps: thread = one query row ----
-    const int quarter = warp & 3;
-    const int r = quarter * 32 + lane;
-    const uint32_t lane_off = (uint32_t)(quarter * 32) << 16;
+    const int r = warp * 32 + lane;
+    const uint32_t lane_off = (uint32_t)(warp * 32) << 16;
     const float c = 0.17677669529663687f * 1.4426950408889634f;   // log2(e)/sqrt(d)
-    uint8_t* prow = smem + A_OFF_P + r * 128;
     const int rsw = r & 7;
-    float m_run = -INFINITY, l_run = 0.f;
-    uint32_t s0[32], s1[32], s2[32], s3[32];
+    const uint32_t prow_s = smem_u32(smem) + A_OFF_P + r * 128;
+    // m_ref is the score the exponent of this row is measured from.  It only follows the running
+    // maximum when that has grown by more than kTau (log2 units): p = 2^((s - m_ref) c) then stays
+    // below 2^kTau, which fp32 sums and bf16 P hold without loss, and the round trip that rescales O
+    // in TMEM (needed on nearly every tile otherwise) becomes rare after the first tiles.
+    constexpr float kTau = 8.0f;
+    float m_ref = -INFINITY, l_run = 0.f;
+    uint32_t s0[32], s1[32], s2[32], s3[16];
     for (int j = 0; j < nkt; ++j) {
-      mbar_wait(s_full, j & 1);
+      const int sb = j & 1;
+      const uint32_t tmem_s = tmem + sb * A_BK + lane_off;
+      if (threadIdx.x == 0) ATTN_TRACE(j * 8 + 0);
+      mbar_wait(&s_full[sb], (j >> 1) & 1);      // S(j) is in TMEM and P buffer sb is free (P V(j-2) done)
       tc_fence_after();
-      // the whole 128-key row of S into registers, then hand the S columns back to the MMA warp
-      tmem_ld32(tmem_s + lane_off + 0, s0);
-      tmem_ld32(tmem_s + lane_off + 32, s1);
-      tmem_ld32(tmem_s + lane_off + 64, s2);
-      tmem_ld32(tmem_s + lane_off + 96, s3);
-      tmem_ld_wait();
+      if (threadIdx.x == 0) ATTN_TRACE(j * 8 + 1);
+      // the whole 112-key row of S into registers, then hand the S columns back to the MMA warp
+      if (!(DBG & 2)) {
+        tmem_ld32(tmem_s + 0, s0);
+        tmem_ld32(tmem_s + 32, s1);
+        tmem_ld32(tmem_s + 64, s2);
+        tmem_ld16(tmem_s + 96, s3);
+        tmem_ld_wait();
+      } else {
+#pragma unroll
+        for (int i = 0; i < 32; ++i) {
+          s0[i] = __float_as_uint(0.01f * (float)(i + j + lane));
+          s1[i] = __float_as_uint(0.02f * (float)(i + j + lane));
+          s2[i] = __float_as_uint(0.03f * (float)(i + j + lane));
+          s3[i & 15] = __float_as_uint(0.04f * (float)(i + j + lane));
+        }
+      }
       tc_fence_before();
-      mbar_arrive(s_free);
+      mbar_arrive(&s_free[sb]);
+      if (threadIdx.x == 0) ATTN_TRACE(j * 8 + 2);
       const int valid = p.n_kv - j * A_BK;       // keys of this tile that exist
       if (valid < A_BK) {                        // last, partial tile only: mask the missing keys
 #pragma unroll
@@ -632,52 +766,86 @@ __global__ void __launch_bounds__(A_THREADS, 2) tc_item_attn_kernel(const __grid
           if (i >= valid) s0[i] = 0xff800000u;
           if (32 + i >= valid) s1[i] = 0xff800000u;
           if (64 + i >= valid) s2[i] = 0xff800000u;
-          if (96 + i >= valid) s3[i] = 0xff800000u;
+          if (i < 16 && 96 + i >= valid) s3[i & 15] = 0xff800000u;
         }
       }
-      float mx = -INFINITY;
+      const uint32_t pbuf = prow_s + sb * A_P_BYTES;
+      const uint64_t c2 = pack_f32x2(c, c);
+      // One pass over the row: p = exp2(s*c - m*c) as bf16 into the 128B-swizzled A tile of the PV MMA
+      // (32 keys = 4 chunks of 16 B inside k-block cc / 2; chunk index XOR (row & 7)), the row sum and,
+      // on the side (ALU pipe, under the MUFU-bound exponentials), the row maximum.
+      float mxa, mxb;
+      auto exp_pass = [&](float mc) -> float {
+        uint64_t lsum2 = 0ull;                                // (0.f, 0.f)
+        const uint64_t nmc2 = pack_f32x2(-mc, -mc);
+        mxa = -INFINITY;
+        mxb = -INFINITY;
+        auto emit = [&](const uint32_t* v, int cc, int n16) {   // n16 = 16-byte chunks (8 keys each) in v
 #pragma unroll
-      for (int i = 0; i < 32; ++i)
-        mx = fmaxf(fmaxf(mx, fmaxf(__uint_as_float(s0[i]), __uint_as_float(s1[i]))),
-                   fmaxf(__uint_as_float(s2[i]), __uint_as_float(s3[i])));
-      const float m_new = fmaxf(m_run, mx);
-      const float alpha = fast_exp2((m_run - m_new) * c);
-      const float mc = m_new * c;
-      // P is double buffered: buffer (j & 1) was last read by PV(j-2), which the wait at the end of
-      // tile j-1 has already covered.
-      // p = exp2(s*c - m*c) as bf16 into the 128B-swizzled A tile of the PV MMA: 32 keys = 4 chunks
-      // of 16 B inside k-block (cc / 2); chunk index XOR (row & 7)
-      float lsum = 0.f;
-      auto emit = [&](const uint32_t (&v)[32], int cc) {
-        uint32_t pk[16];
+          for (int q = 0; q < 4; ++q) {
+            if (q < n16) {
+              uint32_t pk[4];
 #pragma unroll
-        for (int i = 0; i < 16; ++i) {
-          const float a = fast_exp2(fmaf(__uint_as_float(v[2 * i]), c, -mc));
-          const float b = fast_exp2(fmaf(__uint_as_float(v[2 * i + 1]), c, -mc));
-          lsum += a + b;
-          pk[i] = pack_bf16x2(a, b);
-        }
-        uint8_t* kb = prow + (j & 1) * A_P_BYTES + (cc >> 1) * (A_P_BYTES / 2);
-#pragma unroll
-        for (int q = 0; q < 4; ++q) {
-          const int chunk = (cc & 1) * 4 + q;
-          *reinterpret_cast<uint4*>(kb + ((chunk ^ rsw) << 4)) =
-              make_uint4(pk[4 * q], pk[4 * q + 1], pk[4 * q + 2], pk[4 * q + 3]);
-        }
+              for (int i = 0; i < 4; ++i) {
+                const int e = 8 * q + 2 * i;
+                const float sa = __uint_as_float(v[e]), sb2 = __uint_as_float(v[e + 1]);
+                if (!(DBG & 32)) {
+                  if (i & 1) mxb = fmaxf(mxb, fmaxf(sa, sb2));
+                  else mxa = fmaxf(mxa, fmaxf(sa, sb2));
+                }
+                float xa, xb;
+                unpack_f32x2(fma_f32x2(pack_f32x2(sa, sb2), c2, nmc2), xa, xb);
+                const float a = (DBG & 1) ? xa : poly_sel(e, PN) ? poly_exp2(xa) : fast_exp2(xa);
+                const float b = (DBG & 1) ? xb : poly_sel(e + 1, PN) ? poly_exp2(xb) : fast_exp2(xb);
+                lsum2 = add_f32x2(lsum2, pack_f32x2(a, b));
+                pk[i] = pack_bf16x2(a, b);
+              }
+              const uint32_t kb = pbuf + (cc >> 1) * (A_P_BYTES / 2);
+              const int chunk = (cc & 1) * 4 + q;
+              if (!(DBG & 4)) st_shared_v4(kb + ((chunk ^ rsw) << 4), pk[0], pk[1], pk[2], pk[3]);
+              else if (pk[0] == 0x12345678u) l_run += 1.f;     // keep the values alive
+            }
+          }
+        };
+        emit(s0, 0, 4);
+        emit(s1, 1, 4);
+        emit(s2, 2, 4);
+        emit(s3, 3, 2);
+        float lsum0, lsum1;
+        unpack_f32x2(lsum2, lsum0, lsum1);
+        return lsum0 + lsum1;
       };
-      emit(s0, 0);
-      emit(s1, 1);
-      emit(s2, 2);
-      emit(s3, 3);
-      l_run = l_run * alpha + lsum;
-      m_run = m_new;
-      // PV(j-1) must be complete before O is rescaled here and before PV(j) may be issued
-      if (j > 0) {
-        mbar_wait(pv_done, (j - 1) & 1);
-        tc_fence_after();
+      if (j == 0) {
+        // first tile: the reference is the true maximum of the tile
+        float mx0 = -INFINITY, mx1 = -INFINITY, mx2 = -INFINITY, mx3 = -INFINITY;
+#pragma unroll
+        for (int i = 0; i < 32; i += 2) {
+          mx0 = fmaxf(mx0, fmaxf(__uint_as_float(s0[i]), __uint_as_float(s0[i + 1])));
+          mx1 = fmaxf(mx1, fmaxf(__uint_as_float(s1[i]), __uint_as_float(s1[i + 1])));
+          mx2 = fmaxf(mx2, fmaxf(__uint_as_float(s2[i]), __uint_as_float(s2[i + 1])));
+          if (i < 16) mx3 = fmaxf(mx3, fmaxf(__uint_as_float(s3[i & 15]), __uint_as_float(s3[(i + 1) & 15])));
+        }
+        m_ref = fmaxf(fmaxf(mx0, mx1), fmaxf(mx2, mx3));
       }
-      // rescale the running output when some row of this warp moved its maximum
-      if (j > 0 && __any_sync(0xffffffffu, alpha != 1.0f)) {
+      if (threadIdx.x == 0) ATTN_TRACE(j * 8 + 3);
+      // later tiles: exponentials are taken against the reference of the previous tile while the
+      // maximum is still being found; only a row whose maximum then turns out to have grown by more
+      // than kTau redoes its exponentials (rare: the running maximum of n keys moves ~ log n times)
+      float lsum = exp_pass(m_ref * c);
+      const float mx = fmaxf(mxa, mxb);
+      const bool moved = (mx - m_ref) * c > kTau;
+      float alpha = 1.0f;
+      if (moved) {
+        alpha = fast_exp2((m_ref - mx) * c);
+        m_ref = mx;
+        lsum = exp_pass(m_ref * c);
+      }
+      l_run = l_run * alpha + lsum;
+      if (threadIdx.x == 0) ATTN_TRACE(j * 8 + 4);
+      // rescale the running output when some row of this warp moved its reference: needs P V(j-1)
+      if (__any_sync(0xffffffffu, moved)) {
+        mbar_wait(&pv_done[(j - 1) & 1], ((j - 1) >> 1) & 1);   // j >= 1 here: tile 0 never moves
+        tc_fence_after();
         tmem_ld32(tmem_o + lane_off, s0);
         tmem_ld_wait();
 #pragma unroll
@@ -685,12 +853,14 @@ __global__ void __launch_bounds__(A_THREADS, 2) tc_item_attn_kernel(const __grid
         tmem_st32(tmem_o + lane_off, s0);
         tmem_st_wait();
       }
+      if (threadIdx.x == 0) ATTN_TRACE(j * 8 + 6);
       fence_proxy_async();
       tc_fence_before();
-      mbar_arrive(p_full);
+      mbar_arrive(&p_full[sb]);
+      if (threadIdx.x == 0) ATTN_TRACE(j * 8 + 7);
     }
     uint32_t (&v)[32] = s0;
-    mbar_wait(pv_done, (nkt - 1) & 1);
+    mbar_wait(&pv_done[(nkt - 1) & 1], ((nkt - 1) >> 1) & 1);   // tcgen05 ops complete in order: covers all P V
     tc_fence_after();
     tmem_ld32(tmem_o + lane_off, v);
     tmem_ld_wait();
@@ -710,7 +880,7 @@ __global__ void __launch_bounds__(A_THREADS, 2) tc_item_attn_kernel(const __grid
     tc_fence_before();
   }
   __syncthreads();
-  if (warp == 1) {
+  if (warp == 4) {
     tc_fence_after();
     tmem_dealloc(tmem, A_TMEM_COLS);
   }
@@ -743,14 +913,53 @@ int launch_tc_item_attn(const TcItemAttn& p, cudaStream_t st) {
     const cuuint32_t box[3] = {64, kD, 1};
     MMPFN_TRY(encode_map(&mvt, p.vt, 3, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_128B));
   }
-  static bool configured = false;
-  if (!configured) {
-    cudaFuncSetAttribute(tc_item_attn_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, A_SMEM);
-    configured = true;
+  // MMPFN_ATTN_POLY (0..16, read once): how many of every 32 exponentials leave the MUFU pipe for
+  // the FMA-pipe polynomial; the default is the measured optimum.
+  static int poly = -1, dbg = 0;
+  if (poly < 0) {
+    const char* e = getenv("MMPFN_ATTN_POLY");
+    poly = e ? atoi(e) : kAttnPolyDefault;
+    e = getenv("MMPFN_ATTN_DBG");
+    dbg = e ? atoi(e) : 0;
   }
   AttnArgs a{p.out, p.T, p.n_q, p.n_kv, p.shared_kv, q_tiles};
-  tc_item_attn_kernel<<<dim3((unsigned)(planes_q * q_tiles)), A_THREADS, A_SMEM, st>>>(mq, mk, mvt, a);
+  const dim3 grid((unsigned)(planes_q * q_tiles));
+#define MMPFN_ATTN_LAUNCH(PN, DBG)                                                                          \
+  do {                                                                                                      \
+    cudaFuncSetAttribute(tc_item_attn_kernel<PN, DBG>, cudaFuncAttributeMaxDynamicSharedMemorySize, A_SMEM); \
+    tc_item_attn_kernel<PN, DBG><<<grid, A_THREADS, A_SMEM, st>>>(mq, mk, mvt, a);                            \
+  } while (0)
+  if (dbg) {
+    switch (dbg) {
+      case 1: MMPFN_ATTN_LAUNCH(0, 1); break;
+      case 2: MMPFN_ATTN_LAUNCH(0, 2); break;
+      case 4: MMPFN_ATTN_LAUNCH(0, 4); break;
+      case 8: MMPFN_ATTN_LAUNCH(0, 8); break;
+      case 16: MMPFN_ATTN_LAUNCH(0, 16); break;
+      case 32: MMPFN_ATTN_LAUNCH(0, 32); break;
+      case 33: MMPFN_ATTN_LAUNCH(0, 33); break;
+      case 39: MMPFN_ATTN_LAUNCH(0, 39); break;
+      case 24: MMPFN_ATTN_LAUNCH(0, 24); break;
+      case 63: MMPFN_ATTN_LAUNCH(0, 63); break;
+      case 64: MMPFN_ATTN_LAUNCH(0, 64); break;
+      default: set_error("unknown MMPFN_ATTN_DBG"); return MMPFN_EINVAL;
+    }
+    return count_launch();
+  }
+  switch (poly) {
+    case 4: MMPFN_ATTN_LAUNCH(4, 0); break;
+    case 8: MMPFN_ATTN_LAUNCH(8, 0); break;
+    case 12: MMPFN_ATTN_LAUNCH(12, 0); break;
+    default: MMPFN_ATTN_LAUNCH(0, 0); break;
+  }
+#undef MMPFN_ATTN_LAUNCH
   return count_launch();
 }
 
 }  // namespace mmpfn
+
+// debug: copy the clock64 trace of the traced CTA to the host (MMPFN_ATTN_DBG=64 runs)
+extern "C" int mmpfn_debug_attn_trace(long long* host_out, int n) {
+  if (n > 4096) n = 4096;
+  return cudaMemcpyFromSymbol(host_out, mmpfn::g_attn_trace, sizeof(long long) * n) == cudaSuccess ? 0 : MMPFN_ECUDA;
+}
