@@ -181,6 +181,12 @@ int mmpfn_linear_f32(const float* A, const float* W, const float* bias, int M, i
 int mmpfn_linear_bf16(const uint16_t* A, const uint16_t* W, int M, int N, int K, int epi, uint16_t* out,
                       void* stream);
 
+/* The MLP sublayer alone (mlp.py:93-138 + layer.py:437-455), one fused tcgen05 kernel, in place:
+ *   state_f32 [M][192] <- LayerNorm(state_f32 + W2 gelu(W1 state_bf16)),  state_bf16 <- bf16(state_f32)
+ * w1 [768][192], w2 [192][768] bf16 (the reference's linear1.weight / linear2.weight). */
+int mmpfn_mlp_bf16(float* state_f32, uint16_t* state_bf16, const uint16_t* w1, const uint16_t* w2, int M,
+                   void* stream);
+
 /* Item-axis attention alone (layer.py:341-379), bf16 tcgen05 kernel, for unit tests and roofline timing.
  *   q  [B*T*nhead][Sq_pad][32]   k [planes_kv][Skv_pad][32]   vt [planes_kv][32][Skv_pad]   (bf16)
  *   planes_kv = B*T (shared_kv = 1: every query head reads head 0) or B*T*nhead (shared_kv = 0)

@@ -3,6 +3,7 @@
 // host synchronisation; everything is enqueued on the caller's stream.
 #include <stdarg.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include "common.cuh"
@@ -323,6 +324,17 @@ static int mlp(const LayerW& lw, float* state, uint16_t* state_b, long long M, i
     MMPFN_TRY(launch_sgemm(gemm(ws.hid, kHid, lw.w2, kHid, nullptr, ws.tmp, kE, (int)M, kE, kHid), EPI_NONE, st));
     return launch_layernorm(ws.tmp, state, nullptr, nullptr, M, kE, state, nullptr, st);
   }
+  // MMPFN_FUSED_MLP=0 falls back to the two-GEMM form (A/B timing and bisecting only)
+  static int fused = -1;
+  if (fused < 0) {
+    const char* e = getenv("MMPFN_FUSED_MLP");
+    fused = e ? atoi(e) : 1;
+  }
+  if (fused) {
+    TcMlp f{};
+    f.state_b = state_b; f.state_b_out = state_b; f.resid_f32 = state; f.w1 = lw.w1_b; f.w2 = lw.w2_b; f.M = (int)M;
+    return launch_tc_mlp(f, st);
+  }
   TcGemm a{};
   a.A = state_b; a.W = lw.w1_b; a.M = (int)M; a.N = kHid; a.K = kE; a.epi = TC_EPI_GELU_BF16; a.out_bf16 = ws.hid_b;
   MMPFN_TRY(launch_tc_gemm(a, st));
@@ -503,6 +515,15 @@ int mmpfn_linear_bf16(const uint16_t* A, const uint16_t* W, int M, int N, int K,
   TcGemm a{};
   a.A = A; a.W = W; a.M = M; a.N = N; a.K = K; a.epi = epi == 1 ? TC_EPI_GELU_BF16 : TC_EPI_BF16; a.out_bf16 = out;
   return launch_tc_gemm(a, (cudaStream_t)stream);
+}
+
+int mmpfn_mlp_bf16(float* state_f32, uint16_t* state_bf16, const uint16_t* w1, const uint16_t* w2, int M,
+                   void* stream) {
+  MMPFN_TRY(require_device());
+  if (!state_f32 || !state_bf16 || !w1 || !w2 || M < 1) { set_error("mlp_bf16: bad arguments"); return MMPFN_EINVAL; }
+  TcMlp f{};
+  f.state_b = state_bf16; f.state_b_out = state_bf16; f.resid_f32 = state_f32; f.w1 = w1; f.w2 = w2; f.M = M;
+  return launch_tc_mlp(f, (cudaStream_t)stream);
 }
 
 int mmpfn_item_attention_bf16(const uint16_t* q, const uint16_t* k, const uint16_t* vt, int B, int T, int n_q,

@@ -124,6 +124,17 @@ struct TcGemm {
 };
 int launch_tc_gemm(const TcGemm& p, cudaStream_t st);
 
+// Fused MLP sublayer (kernels_mlp.cu): state <- LN(state + W2 gelu(W1 state)), in place.
+struct TcMlp {
+  const uint16_t* state_b;   // bf16 shadow of the state [M][kE] (MMA operand)
+  uint16_t* state_b_out;     // where the new bf16 shadow goes (may alias state_b)
+  float* resid_f32;          // fp32 state [M][kE]: residual in, LayerNorm out
+  const uint16_t* w1;        // [kHid][kE] bf16
+  const uint16_t* w2;        // [kE][kHid] bf16
+  int M;
+};
+int launch_tc_mlp(const TcMlp& p, cudaStream_t st);
+
 struct TcItemAttn {
   const uint16_t* q;    // [planes_q = B*T*kH][Sq_pad][kD]
   const uint16_t* k;    // [planes_kv][Skv_pad][kD]

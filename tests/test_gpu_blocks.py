@@ -75,6 +75,28 @@ def test_linear_bf16_tcgen05(M, N, K, epi):
     assert err < 0.04, err                                          # bf16 output rounding of O(4) values
 
 
+@pytest.mark.parametrize("M", [1, 128, 300, 20000, 62101])
+def test_fused_mlp_tcgen05(M):
+    """state <- LN(state + W2 gelu(W1 state)) (mlp.py:93-138, layer.py:437-455) in one kernel vs fp64 torch
+    on the same bf16 operands.  The hidden activation is rounded to bf16 inside the kernel and the
+    GELU is the tanh-form erf (kernels_mlp.cu): tolerance 0.03 on O(1) LayerNorm outputs."""
+    lib = _lib.load()
+    g = torch.Generator().manual_seed(M)
+    x = torch.randn(M, 192, generator=g).cuda()
+    xb = x.to(torch.bfloat16)
+    w1 = (torch.randn(768, 192, generator=g) / 192 ** 0.5).cuda().to(torch.bfloat16)
+    w2 = (torch.randn(192, 768, generator=g) / 768 ** 0.5).cuda().to(torch.bfloat16)
+    st, stb = x.clone(), xb.clone()
+    _lib.check(lib.mmpfn_mlp_bf16(st.data_ptr(), stb.data_ptr(), w1.data_ptr(), w2.data_ptr(), M, _stream()), "mlp")
+    torch.cuda.synchronize()
+    h = torch.nn.functional.gelu(xb.double() @ w1.double().T)
+    ref = torch.nn.functional.layer_norm(x.double() + h @ w2.double().T, (192,), None, None, 1e-5)
+    e1 = (st.double() - ref).abs().max().item()
+    e2 = (stb.double() - ref).abs().max().item()
+    assert not torch.isnan(st).any()
+    assert e1 < 0.03 and e2 < 0.05, (e1, e2)
+
+
 def _one_layer_model(precision, seed=3):
     from multimodalpfn_b200.model import B200PerFeatureTransformer
     geom = Geometry(nlayers=1, mgm_heads=2, cap_heads=4)
