@@ -490,90 +490,95 @@ __global__ void __launch_bounds__(A_THREADS, 2) tc_item_attn_kernel(const __grid
     // below 2^kTau, which fp32 sums and bf16 P hold without loss, and the round trip that rescales O
     // in TMEM (needed on nearly every tile otherwise) becomes rare after the first tiles.
     constexpr float kTau = 8.0f;
+    constexpr int kNP = A_BK / 2;                // 56 pairs of keys per row and tile
+    constexpr int kAhead = 4;                    // pairs whose scaled argument is ready ahead of their ex2
+    constexpr int kBehind = 5;                   // pairs whose ex2 is in flight before the first consumer reads one
     float m_ref = -INFINITY, l_run = 0.f;
     uint32_t s0[32], s1[32], s2[32], s3[16];
+    // element e of the row (compile-time index after unrolling)
+#define S_AT(e) ((e) < 32 ? s0[(e) & 31] : (e) < 64 ? s1[(e) & 31] : (e) < 96 ? s2[(e) & 31] : s3[(e) & 15])
     for (int j = 0; j < nkt; ++j) {
       const int sb = j & 1;
       const uint32_t tmem_s = tmem + sb * A_BK + lane_off;
+      const uint32_t pbuf = prow_s + sb * A_P_BYTES;
+      const int valid = p.n_kv - j * A_BK;       // keys of this tile that exist
       if (threadIdx.x == 0) ATTN_TRACE(j * 8 + 0);
       mbar_wait(&s_full[sb], (j >> 1) & 1);      // S(j) is in TMEM and P buffer sb is free (P V(j-2) done)
       tc_fence_after();
       if (threadIdx.x == 0) ATTN_TRACE(j * 8 + 1);
-      // the whole 112-key row of S into registers, then hand the S columns back to the MMA warp
-      if (!(DBG & 2)) {
+      // the whole 112-key row of S into registers (masking the keys a partial last tile does not have)
+      auto load_row = [&]() {
         tmem_ld32(tmem_s + 0, s0);
         tmem_ld32(tmem_s + 32, s1);
         tmem_ld32(tmem_s + 64, s2);
         tmem_ld16(tmem_s + 96, s3);
         tmem_ld_wait();
-      } else {
+        if (valid < A_BK) {
 #pragma unroll
-        for (int i = 0; i < 32; ++i) {
-          s0[i] = __float_as_uint(0.01f * (float)(i + j + lane));
-          s1[i] = __float_as_uint(0.02f * (float)(i + j + lane));
-          s2[i] = __float_as_uint(0.03f * (float)(i + j + lane));
-          s3[i & 15] = __float_as_uint(0.04f * (float)(i + j + lane));
+          for (int i = 0; i < 32; ++i) {
+            if (i >= valid) s0[i] = 0xff800000u;
+            if (32 + i >= valid) s1[i] = 0xff800000u;
+            if (64 + i >= valid) s2[i] = 0xff800000u;
+            if (i < 16 && 96 + i >= valid) s3[i & 15] = 0xff800000u;
+          }
         }
-      }
-      tc_fence_before();
-      mbar_arrive(&s_free[sb]);
-      if (threadIdx.x == 0) ATTN_TRACE(j * 8 + 2);
-      const int valid = p.n_kv - j * A_BK;       // keys of this tile that exist
-      if (valid < A_BK) {                        // last, partial tile only: mask the missing keys
-#pragma unroll
-        for (int i = 0; i < 32; ++i) {
-          if (i >= valid) s0[i] = 0xff800000u;
-          if (32 + i >= valid) s1[i] = 0xff800000u;
-          if (64 + i >= valid) s2[i] = 0xff800000u;
-          if (i < 16 && 96 + i >= valid) s3[i & 15] = 0xff800000u;
-        }
-      }
-      const uint32_t pbuf = prow_s + sb * A_P_BYTES;
-      const uint64_t c2 = pack_f32x2(c, c);
-      // One pass over the row: p = exp2(s*c - m*c) as bf16 into the 128B-swizzled A tile of the PV MMA
-      // (32 keys = 4 chunks of 16 B inside k-block cc / 2; chunk index XOR (row & 7)), the row sum and,
-      // on the side (ALU pipe, under the MUFU-bound exponentials), the row maximum.
+      };
+      // One software-pipelined sweep over the row, written so that a lone warp keeps the MUFU pipe fed:
+      // step k scales pair k+kAhead (FFMA2, and folds it into the row maximum, FMNMX3), starts the two
+      // ex2 of pair k, and retires pair k-kBehind (row sum FADD2, bf16 pack F2FP, every fourth pair a
+      // 16-byte store into the 128B-swizzled A tile of the PV MMA: 8 keys = one chunk of the row's
+      // 128 B k-block line, chunk index XOR (row & 7)).  Values are transformed in place: s -> x -> p.
       float mxa, mxb;
-      auto exp_pass = [&](float mc) -> float {
-        uint64_t lsum2 = 0ull;                                // (0.f, 0.f)
+      const uint64_t c2 = pack_f32x2(c, c);
+      auto sweep = [&](float mc) -> float {
         const uint64_t nmc2 = pack_f32x2(-mc, -mc);
+        uint64_t lsum2 = 0ull;                                // (0.f, 0.f)
+        uint32_t pk[4];
         mxa = -INFINITY;
         mxb = -INFINITY;
-        auto emit = [&](const uint32_t* v, int cc, int n16) {   // n16 = 16-byte chunks (8 keys each) in v
-#pragma unroll
-          for (int q = 0; q < 4; ++q) {
-            if (q < n16) {
-              uint32_t pk[4];
-#pragma unroll
-              for (int i = 0; i < 4; ++i) {
-                const int e = 8 * q + 2 * i;
-                const float sa = __uint_as_float(v[e]), sb2 = __uint_as_float(v[e + 1]);
-                if (!(DBG & 32)) {
-                  if (i & 1) mxb = fmaxf(mxb, fmaxf(sa, sb2));
-                  else mxa = fmaxf(mxa, fmaxf(sa, sb2));
-                }
-                float xa, xb;
-                unpack_f32x2(fma_f32x2(pack_f32x2(sa, sb2), c2, nmc2), xa, xb);
-                const float a = (DBG & 1) ? xa : poly_sel(e, PN) ? poly_exp2(xa) : fast_exp2(xa);
-                const float b = (DBG & 1) ? xb : poly_sel(e + 1, PN) ? poly_exp2(xb) : fast_exp2(xb);
-                lsum2 = add_f32x2(lsum2, pack_f32x2(a, b));
-                pk[i] = pack_bf16x2(a, b);
-              }
-              const uint32_t kb = pbuf + (cc >> 1) * (A_P_BYTES / 2);
-              const int chunk = (cc & 1) * 4 + q;
-              if (!(DBG & 4)) st_shared_v4(kb + ((chunk ^ rsw) << 4), pk[0], pk[1], pk[2], pk[3]);
-              else if (pk[0] == 0x12345678u) l_run += 1.f;     // keep the values alive
-            }
+        auto scale = [&](int k) {
+          const float sa = __uint_as_float(S_AT(2 * k)), sb2 = __uint_as_float(S_AT(2 * k + 1));
+          if (!(DBG & 32)) {
+            if (k & 1) mxb = fmaxf(mxb, fmaxf(sa, sb2));
+            else mxa = fmaxf(mxa, fmaxf(sa, sb2));
+          }
+          float xa, xb;
+          unpack_f32x2(fma_f32x2(pack_f32x2(sa, sb2), c2, nmc2), xa, xb);
+          S_AT(2 * k) = __float_as_uint(xa);
+          S_AT(2 * k + 1) = __float_as_uint(xb);
+        };
+        auto expo = [&](int k) {
+          const float xa = __uint_as_float(S_AT(2 * k)), xb = __uint_as_float(S_AT(2 * k + 1));
+          const float a = (DBG & 1) ? xa : poly_sel((2 * k) & 31, PN) ? poly_exp2(xa) : fast_exp2(xa);
+          const float b = (DBG & 1) ? xb : poly_sel((2 * k + 1) & 31, PN) ? poly_exp2(xb) : fast_exp2(xb);
+          S_AT(2 * k) = __float_as_uint(a);
+          S_AT(2 * k + 1) = __float_as_uint(b);
+        };
+        auto retire = [&](int k) {
+          const float a = __uint_as_float(S_AT(2 * k)), b = __uint_as_float(S_AT(2 * k + 1));
+          lsum2 = add_f32x2(lsum2, pack_f32x2(a, b));
+          pk[k & 3] = pack_bf16x2(a, b);
+          if ((k & 3) == 3) {
+            const int c16 = k >> 2;                           // 16-byte chunk of the row: keys 8*c16 .. +7
+            const uint32_t kb = pbuf + (c16 >> 3) * (A_P_BYTES / 2);
+            if (!(DBG & 4)) st_shared_v4(kb + (((c16 & 7) ^ rsw) << 4), pk[0], pk[1], pk[2], pk[3]);
+            else if (pk[0] == 0x12345678u) l_run += 1.f;     // keep the values alive
           }
         };
-        emit(s0, 0, 4);
-        emit(s1, 1, 4);
-        emit(s2, 2, 4);
-        emit(s3, 3, 2);
+#pragma unroll
+        for (int k = 0; k < kAhead; ++k) scale(k);
+#pragma unroll
+        for (int k = 0; k < kNP + kBehind; ++k) {
+          if (k + kAhead < kNP) scale(k + kAhead);
+          if (k < kNP) expo(k);
+          if (k >= kBehind) retire(k - kBehind);
+        }
         float lsum0, lsum1;
         unpack_f32x2(lsum2, lsum0, lsum1);
         return lsum0 + lsum1;
       };
+      if (!(DBG & 2)) load_row();
+      if (threadIdx.x == 0) ATTN_TRACE(j * 8 + 2);
       if (j == 0) {
         // first tile: the reference is the true maximum of the tile
         float mx0 = -INFINITY, mx1 = -INFINITY, mx2 = -INFINITY, mx3 = -INFINITY;
@@ -588,21 +593,29 @@ __global__ void __launch_bounds__(A_THREADS, 2) tc_item_attn_kernel(const __grid
       }
       if (threadIdx.x == 0) ATTN_TRACE(j * 8 + 3);
       // later tiles: exponentials are taken against the reference of the previous tile while the
-      // maximum is still being found; only a row whose maximum then turns out to have grown by more
-      // than kTau redoes its exponentials (rare: the running maximum of n keys moves ~ log n times)
-      float lsum = exp_pass(m_ref * c);
+      // maximum is still being found; only when a row's maximum then turns out to have grown by more
+      // than kTau is the sweep repeated (rare: the running maximum of n keys moves ~ log n times).
+      // S was consumed in place, so the repeat reads it from TMEM again: the S columns are handed
+      // back to the MMA warp only after the decision (S is double buffered: no one is waiting).
+      float lsum = sweep(m_ref * c);
       const float mx = fmaxf(mxa, mxb);
       const bool moved = (mx - m_ref) * c > kTau;
+      const bool any_moved = __any_sync(0xffffffffu, moved);   // tcgen05.ld is warp-collective
       float alpha = 1.0f;
-      if (moved) {
-        alpha = fast_exp2((m_ref - mx) * c);
-        m_ref = mx;
-        lsum = exp_pass(m_ref * c);
+      if (any_moved) {
+        if (moved) {
+          alpha = fast_exp2((m_ref - mx) * c);
+          m_ref = mx;
+        }
+        load_row();
+        lsum = sweep(m_ref * c);
       }
+      tc_fence_before();
+      mbar_arrive(&s_free[sb]);
       l_run = l_run * alpha + lsum;
       if (threadIdx.x == 0) ATTN_TRACE(j * 8 + 4);
       // rescale the running output when some row of this warp moved its reference: needs P V(j-1)
-      if (__any_sync(0xffffffffu, moved)) {
+      if (any_moved) {
         mbar_wait(&pv_done[(j - 1) & 1], ((j - 1) >> 1) & 1);   // j >= 1 here: tile 0 never moves
         tc_fence_after();
         tmem_ld32(tmem_o + lane_off, s0);
@@ -618,6 +631,7 @@ __global__ void __launch_bounds__(A_THREADS, 2) tc_item_attn_kernel(const __grid
       mbar_arrive(&p_full[sb]);
       if (threadIdx.x == 0) ATTN_TRACE(j * 8 + 7);
     }
+#undef S_AT
     uint32_t (&v)[32] = s0;
     mbar_wait(&pv_done[(nkt - 1) & 1], ((nkt - 1) >> 1) & 1);   // tcgen05 ops complete in order: covers all P V
     tc_fence_after();
