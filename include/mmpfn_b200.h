@@ -181,6 +181,12 @@ int mmpfn_linear_f32(const float* A, const float* W, const float* bias, int M, i
 int mmpfn_linear_bf16(const uint16_t* A, const uint16_t* W, int M, int N, int K, int epi, uint16_t* out,
                       void* stream);
 
+/* An attention output projection with its residual + LayerNorm (multi_head_attention.py:513-517,
+ * layer.py:437-455), one persistent tcgen05 kernel, in place:
+ *   state_f32 [M][192] <- LayerNorm(state_f32 + A W^T),  state_bf16 <- bf16(state_f32);  A [M][192], W [192][192] bf16. */
+int mmpfn_linear_ln_bf16(const uint16_t* A, const uint16_t* W, int M, float* state_f32, uint16_t* state_bf16,
+                         void* stream);
+
 /* The MLP sublayer alone (mlp.py:93-138 + layer.py:437-455), one fused tcgen05 kernel, in place:
  *   state_f32 [M][192] <- LayerNorm(state_f32 + W2 gelu(W1 state_bf16)),  state_bf16 <- bf16(state_f32)
  * w1 [768][192], w2 [192][768] bf16 (the reference's linear1.weight / linear2.weight). */

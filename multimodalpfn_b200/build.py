@@ -16,7 +16,7 @@ CSRC = os.path.join(HERE, "csrc")
 INCLUDE = os.path.join(os.path.dirname(HERE), "include")
 LIB = os.path.join(HERE, "libmmpfn_b200.so")
 STAMP = os.path.join(HERE, ".libmmpfn_b200.stamp")
-SOURCES = ["api.cu", "kernels_f32.cu", "kernels_stem.cu", "kernels_tc.cu", "kernels_mlp.cu"]
+SOURCES = ["api.cu", "kernels_f32.cu", "kernels_stem.cu", "kernels_tc.cu", "kernels_attn.cu", "kernels_mlp.cu", "kernels_rowgemm.cu"]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
     "--expt-relaxed-constexpr", "-Xcompiler", "-fPIC", "-shared", "-cudart", "static",

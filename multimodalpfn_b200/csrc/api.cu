@@ -92,6 +92,17 @@ static LayerW layer_w(const mmpfn_weights* w, int l) {
 
 static int kv_pad(int n) { return (n + 63) / 64 * 64; }
 
+// K = 192 projections: the persistent kernel (kernels_rowgemm.cu); MMPFN_ROWGEMM=0 selects the
+// one-tile-per-CTA kernel of kernels_tc.cu instead (A/B timing and bisecting only).
+static int proj_gemm(const TcGemm& g, cudaStream_t st) {
+  static int persistent = -1;
+  if (persistent < 0) {
+    const char* e = getenv("MMPFN_ROWGEMM");
+    persistent = e ? atoi(e) : 1;
+  }
+  return persistent ? launch_tc_rowgemm(g, st) : launch_tc_gemm(g, st);
+}
+
 // workspace carving for the layers
 struct LayerWs {
   // fp32 mode
@@ -309,12 +320,12 @@ static int feature_attention(const LayerW& lw, float* state, uint16_t* state_b, 
   }
   TcGemm a{};
   a.A = state_b; a.W = lw.fqkv_b; a.M = (int)M; a.N = 3 * kE; a.K = kE; a.epi = TC_EPI_BF16; a.out_bf16 = ws.qkv_b;
-  MMPFN_TRY(launch_tc_gemm(a, st));
+  MMPFN_TRY(proj_gemm(a, st));
   MMPFN_TRY(launch_feat_attn_bf16(ws.qkv_b, ws.att_b, n_seq, T, st));
   TcGemm o{};
   o.A = ws.att_b; o.W = lw.fout_b; o.M = (int)M; o.N = kE; o.K = kE; o.epi = TC_EPI_RESID_LN;
   o.resid_f32 = state; o.ln_bf16 = state_b;
-  return launch_tc_gemm(o, st);
+  return proj_gemm(o, st);
 }
 
 static int mlp(const LayerW& lw, float* state, uint16_t* state_b, long long M, int precision, const LayerWs& ws,
@@ -353,7 +364,7 @@ static int out_proj_ln(const LayerW& lw, float* state, uint16_t* state_b, long l
   TcGemm o{};
   o.A = ws.att_b; o.W = lw.iout_b; o.M = (int)M; o.N = kE; o.K = kE; o.epi = TC_EPI_RESID_LN;
   o.resid_f32 = state; o.ln_bf16 = state_b;
-  return launch_tc_gemm(o, st);
+  return proj_gemm(o, st);
 }
 
 static int check_layers_args(const mmpfn_geometry* g, const mmpfn_weights* w, float* state, uint16_t* state_b, int B,
@@ -413,7 +424,7 @@ int mmpfn_layers_train(const mmpfn_geometry* g, const mmpfn_weights* w, float* s
         q.k0_out = kvl;
         q.vt0_out = kvl + (size_t)B * T * Sp * kD;
       }
-      MMPFN_TRY(launch_tc_gemm(q, st));
+      MMPFN_TRY(proj_gemm(q, st));
       TcItemAttn a{};
       a.q = ws.qi; a.k = ws.ki; a.vt = ws.vti; a.out = ws.att_b;
       a.B = B; a.T = T; a.n_q = S; a.Sq_pad = Sp; a.n_kv = S; a.Skv_pad = Sp; a.shared_kv = 0;
@@ -452,7 +463,7 @@ int mmpfn_layers_test(const mmpfn_geometry* g, const mmpfn_weights* w, float* st
       TcGemm q{};
       q.A = state_b; q.W = lw.iqkv_b; q.N = kE; q.K = kE; q.items = 1; q.B = B; q.S = S; q.T = T;
       q.epi = TC_EPI_QKV_ITEMS; q.q_out = ws.qi; q.S_pad = Sp;
-      MMPFN_TRY(launch_tc_gemm(q, st));
+      MMPFN_TRY(proj_gemm(q, st));
       const uint16_t* kvl = (const uint16_t*)kv + (size_t)l * B * T * Np * 2 * kD;
       TcItemAttn a{};
       a.q = ws.qi; a.k = kvl; a.vt = kvl + (size_t)B * T * Np * kD; a.out = ws.att_b;
@@ -514,7 +525,17 @@ int mmpfn_linear_bf16(const uint16_t* A, const uint16_t* W, int M, int N, int K,
   if (!A || !W || !out || (epi != 0 && epi != 1)) { set_error("linear_bf16: bad arguments"); return MMPFN_EINVAL; }
   TcGemm a{};
   a.A = A; a.W = W; a.M = M; a.N = N; a.K = K; a.epi = epi == 1 ? TC_EPI_GELU_BF16 : TC_EPI_BF16; a.out_bf16 = out;
+  if (epi == 0 && K == kE && N % kE == 0) return proj_gemm(a, (cudaStream_t)stream);
   return launch_tc_gemm(a, (cudaStream_t)stream);
+}
+
+int mmpfn_linear_ln_bf16(const uint16_t* A, const uint16_t* W, int M, float* state_f32, uint16_t* state_bf16,
+                         void* stream) {
+  MMPFN_TRY(require_device());
+  if (!A || !W || !state_f32 || !state_bf16 || M < 1) { set_error("linear_ln_bf16: bad arguments"); return MMPFN_EINVAL; }
+  TcGemm o{};
+  o.A = A; o.W = W; o.M = M; o.N = kE; o.K = kE; o.epi = TC_EPI_RESID_LN; o.resid_f32 = state_f32; o.ln_bf16 = state_bf16;
+  return proj_gemm(o, (cudaStream_t)stream);
 }
 
 int mmpfn_mlp_bf16(float* state_f32, uint16_t* state_bf16, const uint16_t* w1, const uint16_t* w2, int M,

@@ -123,6 +123,8 @@ struct TcGemm {
   uint16_t *k0_out, *vt0_out;
 };
 int launch_tc_gemm(const TcGemm& p, cudaStream_t st);
+// persistent variant for K = 192, N % 192 == 0 (kernels_rowgemm.cu): BF16 / RESID_LN / QKV_ITEMS epilogues
+int launch_tc_rowgemm(const TcGemm& p, cudaStream_t st);
 
 // Fused MLP sublayer (kernels_mlp.cu): state <- LN(state + W2 gelu(W1 state)), in place.
 struct TcMlp {

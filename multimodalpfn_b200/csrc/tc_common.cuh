@@ -61,6 +61,14 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
     else if (now - t0 > 4000000000LL) mbar_timeout();
   }
 }
+// One lane of a converged warp.  Guarding a single-thread role with elect.sync (instead of lane == 0) lets
+// ptxas know that exactly one thread is active inside: the uniform-register operands of UTCHMMA / UTMALDG
+// are then filled by plain R2UR moves instead of a per-operand election loop (~70 cycles per MMA issue).
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(pred));
+  return pred != 0;
+}
 __device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
@@ -84,6 +92,10 @@ __device__ __forceinline__ void tma_load_4d(void* dst, const CUtensorMap* map, u
       "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
       ::"r"(smem_u32(dst)), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "r"(c2), "r"(c3)
       : "memory");
+}
+// bytes (a multiple of 16, 16-byte aligned address) of global memory into L2, asynchronously
+__device__ __forceinline__ void l2_prefetch(const void* gptr, uint32_t bytes) {
+  asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(gptr), "r"(bytes) : "memory");
 }
 __device__ __forceinline__ void prefetch_tmap(const CUtensorMap* map) {
   asm volatile("prefetch.tensormap [%0];" ::"l"(map) : "memory");
@@ -193,6 +205,22 @@ __device__ __forceinline__ void st_shared_v4(uint32_t saddr, uint32_t a, uint32_
   asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(saddr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
 }
 
+// ---- epilogue staging: shared memory -> global by TMA (bulk async-group), named barrier of the 128 epilogue threads
+__device__ __forceinline__ void tma_store_2d(const CUtensorMap* map, const void* src, int c0, int c1) {
+  asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];"
+               ::"l"(map), "r"(smem_u32(src)), "r"(c0), "r"(c1) : "memory");
+}
+__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait_read0() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait0() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+__device__ __forceinline__ void epi_bar() { asm volatile("bar.sync 1, 128;" ::: "memory"); }
+
+__device__ __forceinline__ float4 lds128(uint32_t saddr) {
+  float4 v;
+  asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(saddr));
+  return v;
+}
+
 // UMMA shared-memory operand descriptor, K-major, swizzled (cute::UMMA::SmemDescriptor layout):
 // start address >> 4 in [0,14), LBO (=1, unused for swizzled K-major) in [16,30), SBO >> 4 in [32,46),
 // version 1 in [46,48), layout type in [61,64) (2 = 128B swizzle, 4 = 64B swizzle).
@@ -233,13 +261,14 @@ EncodeTiledFn get_encode() {
   return fn;
 }
 
-// bf16 tensor, dims innermost first; strides in bytes for dims 1..rank-1
+// dims innermost first; strides in bytes for dims 1..rank-1; elements are bf16 unless dtype says otherwise
 int encode_map(CUtensorMap* m, const void* base, int rank, const cuuint64_t* dims, const cuuint64_t* strides,
-               const cuuint32_t* box, CUtensorMapSwizzle sw) {
+               const cuuint32_t* box, CUtensorMapSwizzle sw,
+               CUtensorMapDataType dtype = CU_TENSOR_MAP_DATA_TYPE_BFLOAT16) {
   EncodeTiledFn fn = get_encode();
   if (!fn) { set_error("cuTensorMapEncodeTiled not available"); return MMPFN_ECUDA; }
   cuuint32_t ones[5] = {1, 1, 1, 1, 1};
-  CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, (cuuint32_t)rank, const_cast<void*>(base), dims, strides, box,
+  CUresult r = fn(m, dtype, (cuuint32_t)rank, const_cast<void*>(base), dims, strides, box,
                   ones, CU_TENSOR_MAP_INTERLEAVE_NONE, sw, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) {

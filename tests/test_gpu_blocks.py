@@ -97,6 +97,26 @@ def test_fused_mlp_tcgen05(M):
     assert e1 < 0.03 and e2 < 0.05, (e1, e2)
 
 
+@pytest.mark.parametrize("M", [1, 127, 128, 300, 18945, 62101])
+def test_out_projection_layernorm_tcgen05(M):
+    """state <- LN(state + A W^T) (multi_head_attention.py:513-517 + layer.py:437-455): the persistent
+    tcgen05 kernel (resident W, TMA-staged fp32 residual ring) vs fp64 torch on the same bf16 operands."""
+    lib = _lib.load()
+    g = torch.Generator().manual_seed(M + 11)
+    x = torch.randn(M, 192, generator=g).cuda()
+    a = torch.randn(M, 192, generator=g).cuda().to(torch.bfloat16)
+    w = (torch.randn(192, 192, generator=g) / 192 ** 0.5).cuda().to(torch.bfloat16)
+    st, stb = x.clone(), torch.full((M, 192), float("nan"), dtype=torch.bfloat16, device="cuda")
+    _lib.check(lib.mmpfn_linear_ln_bf16(a.data_ptr(), w.data_ptr(), M, st.data_ptr(), stb.data_ptr(), _stream()),
+               "linear_ln")
+    torch.cuda.synchronize()
+    ref = torch.nn.functional.layer_norm(x.double() + a.double() @ w.double().T, (192,), None, None, 1e-5)
+    e1 = (st.double() - ref).abs().max().item()
+    e2 = (stb.double() - ref).abs().max().item()
+    assert not torch.isnan(st).any() and not torch.isnan(stb.float()).any()
+    assert e1 < 2e-4 and e2 < 0.03, (e1, e2)        # fp32 accumulation; bf16 rounding of O(4) values
+
+
 def _one_layer_model(precision, seed=3):
     from multimodalpfn_b200.model import B200PerFeatureTransformer
     geom = Geometry(nlayers=1, mgm_heads=2, cap_heads=4)
