@@ -136,8 +136,8 @@ __global__ void __launch_bounds__(A_THREADS, AttnCfg<BK>::kMinCtas)
       mbar_init(&v_full[s], 1);
       mbar_init(&v_empty[s], 1);
       mbar_init(&s_full[s], 1);
-      mbar_init(&s_free[s], 128);
-      mbar_init(&p_full[s], 128);
+      mbar_init(&s_free[s], 4);
+      mbar_init(&p_full[s], 4);
       mbar_init(&pv_done[s], 1);
     }
     fence_barrier_init();
@@ -209,15 +209,14 @@ __global__ void __launch_bounds__(A_THREADS, AttnCfg<BK>::kMinCtas)
         const uint32_t ph = (j >> 1) & 1;
         if (j + 2 < nkt) {
           // the TMA wait first: it is long satisfied and must not sit behind the softmax hand-off
-          mbar_wait(&k_full[s], ph ^ 1);         // K(j+2): completion (j+2)/2 of slot s
-          mbar_wait(&s_free[s], ph);             // S(j) is in the softmax registers: its columns are free
+          // K(j+2): completion (j+2)/2 of slot s; S(j) is in the softmax registers: its columns are free
+          mbar_wait2(&k_full[s], ph ^ 1, &s_free[s], ph);
           tc_fence_after();
           ATTN_TRACE(2048 + j * 4 + 0);
           issue_s(j + 2);
           ATTN_TRACE(2048 + j * 4 + 1);
         }
-        mbar_wait(&v_full[s], ph);
-        mbar_wait(&p_full[s], ph);               // P(j) is in shared memory
+        mbar_wait2(&v_full[s], ph, &p_full[s], ph);      // V^T(j) landed; P(j) is in shared memory
         tc_fence_after();
         ATTN_TRACE(2048 + j * 4 + 2);
         if (!(DBG & 8)) {
@@ -360,7 +359,7 @@ __global__ void __launch_bounds__(A_THREADS, AttnCfg<BK>::kMinCtas)
         lsum = sweep(m_ref * c);
       }
       tc_fence_before();
-      mbar_arrive(&s_free[sb]);
+      mbar_arrive_warp(&s_free[sb]);
       l_run = l_run * alpha + lsum;
       if (threadIdx.x == 0) ATTN_TRACE(j * 8 + 4);
       // rescale the running output when some row of this warp moved its reference: needs P V(j-1)
@@ -378,7 +377,7 @@ __global__ void __launch_bounds__(A_THREADS, AttnCfg<BK>::kMinCtas)
       if (threadIdx.x == 0) ATTN_TRACE(j * 8 + 6);
       fence_proxy_async();
       tc_fence_before();
-      mbar_arrive(&p_full[sb]);
+      mbar_arrive_warp(&p_full[sb]);
       if (threadIdx.x == 0) ATTN_TRACE(j * 8 + 7);
     }
     uint32_t v[32];
@@ -473,17 +472,17 @@ int launch_tc_item_attn(const TcItemAttn& p, cudaStream_t st) {
   if (p.n_kv <= 0) { set_error("item attention: empty key set"); return MMPFN_EINVAL; }
   // MMPFN_ATTN_POLY (0..16, read once): how many of every 32 exponentials leave the MUFU pipe for
   // the FMA-pipe polynomial; MMPFN_ATTN_BK: keys per tile (112 or 48).  Defaults = measured optimum.
-  static int poly = -1, dbg = 0, bk = 112;
+  static int poly = -1, dbg = 0, bk = 48;
   if (poly < 0) {
     const char* e = getenv("MMPFN_ATTN_POLY");
     poly = e ? atoi(e) : kAttnPolyDefault;
     e = getenv("MMPFN_ATTN_DBG");
     dbg = e ? atoi(e) : 0;
     e = getenv("MMPFN_ATTN_BK");
-    bk = e ? atoi(e) : 112;
+    bk = e ? atoi(e) : 48;
   }
-  if (bk == 48) return launch_attn_bk<48>(p, poly, dbg, st);
-  return launch_attn_bk<112>(p, poly, dbg, st);
+  if (bk == 112) return launch_attn_bk<112>(p, poly, dbg, st);
+  return launch_attn_bk<48>(p, poly, dbg, st);
 }
 
 }  // namespace mmpfn

@@ -17,7 +17,7 @@
 //   warp 1        GEMM1 issue
 //   warp 2        TMEM allocation, then TMA producer of the fp32 residual chunks
 //   warp 3        GEMM2 issue
-//   warps 4-11    GELU: TMEM lane quarter = warp % 4, column half = (warp - 4) / 4
+//   warps 4-11    GELU: TMEM lane quarter = warp % 4, chunk parity = (warp - 4) / 4
 //   warps 12-15   epilogue: residual + LayerNorm, thread = token row
 //
 // The epilogue never touches global memory with thread-private accesses (16-byte pieces at a 768-byte
@@ -119,15 +119,15 @@ __global__ void __launch_bounds__(F_THREADS, 1) tc_mlp_kernel(const __grid_const
   uint64_t* w1_full = bars + 4;        // [2] W1 chunk landed
   uint64_t* w1_empty = bars + 6;       // [2] ... and GEMM1 of its chunk has completed
   uint64_t* h_full = bars + 8;         // [2] hidden chunk accumulator complete in TMEM
-  uint64_t* h_free = bars + 10;        // [2] ... and read out by the GELU warps (256 arrivals)
-  uint64_t* hs_full = bars + 12;       // [2] gelu(chunk) is in shared memory (256 arrivals)
+  uint64_t* h_free = bars + 10;        // [2] ... and read out by the GELU warps (one arrival per warp: 4)
+  uint64_t* hs_full = bars + 12;       // [2] gelu(chunk) is in shared memory (one arrival per warp: 4)
   uint64_t* hs_empty = bars + 14;      // [2] ... and GEMM2 has consumed it
   uint64_t* out_full = bars + 16;      // [2] output accumulator of a tile complete
-  uint64_t* out_empty = bars + 18;     // [2] ... and drained by the epilogue (128 arrivals)
+  uint64_t* out_empty = bars + 18;     // [2] ... and drained by the epilogue (one arrival per warp: 4)
   uint64_t* w2_full = bars + 20;       // [2] W2 chunk landed
   uint64_t* w2_empty = bars + 22;      // [2] ... and GEMM2 of its chunk has completed
   uint64_t* r_full = bars + 24;        // [3] residual chunk landed
-  uint64_t* r_empty = bars + 27;       // [3] ... and its slot may be refilled (128 arrivals)
+  uint64_t* r_empty = bars + 27;       // [3] ... and its slot may be refilled (one arrival per warp: 4)
   uint32_t* tmem_slot = (uint32_t*)(bars + 30);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -145,7 +145,7 @@ __global__ void __launch_bounds__(F_THREADS, 1) tc_mlp_kernel(const __grid_const
     mbar_init(a_empty, 1);
     for (int s = 0; s < F_R_SLOTS; ++s) {
       mbar_init(&r_full[s], 1);
-      mbar_init(&r_empty[s], 128);
+      mbar_init(&r_empty[s], 4);
     }
     for (int s = 0; s < 2; ++s) {
       mbar_init(&w1_full[s], 1);
@@ -153,11 +153,11 @@ __global__ void __launch_bounds__(F_THREADS, 1) tc_mlp_kernel(const __grid_const
       mbar_init(&w2_full[s], 1);
       mbar_init(&w2_empty[s], 1);
       mbar_init(&h_full[s], 1);
-      mbar_init(&h_free[s], 256);
-      mbar_init(&hs_full[s], 256);
+      mbar_init(&h_free[s], 4);
+      mbar_init(&hs_full[s], 4);
       mbar_init(&hs_empty[s], 1);
       mbar_init(&out_full[s], 1);
-      mbar_init(&out_empty[s], 128);
+      mbar_init(&out_empty[s], 4);
     }
     fence_barrier_init();
   }
@@ -231,9 +231,8 @@ __global__ void __launch_bounds__(F_THREADS, 1) tc_mlp_kernel(const __grid_const
         const int hb = g & 1;
         MLP_TRACE(g * 8 + 0);
         if (c == 0) mbar_wait(a_full, i & 1);
-        mbar_wait(&w1_full[hb], (g >> 1) & 1);
+        mbar_wait2(&w1_full[hb], (g >> 1) & 1, &h_free[hb], ((g >> 1) & 1) ^ 1);
         MLP_TRACE(g * 8 + 1);
-        mbar_wait(&h_free[hb], ((g >> 1) & 1) ^ 1);
         MLP_TRACE(g * 8 + 2);
         tc_fence_after();
         const uint32_t a_addr = sbase + F_OFF_A;
@@ -263,9 +262,8 @@ __global__ void __launch_bounds__(F_THREADS, 1) tc_mlp_kernel(const __grid_const
         const int hb = g & 1, ob = i & 1;
         MLP_TRACE(g * 8 + 4);
         if (c == 0) mbar_wait(&out_empty[ob], ((i >> 1) & 1) ^ 1);
-        mbar_wait(&w2_full[hb], (g >> 1) & 1);
+        mbar_wait2(&w2_full[hb], (g >> 1) & 1, &hs_full[hb], (g >> 1) & 1);
         MLP_TRACE(g * 8 + 5);
-        mbar_wait(&hs_full[hb], (g >> 1) & 1);
         MLP_TRACE(g * 8 + 6);
         tc_fence_after();
         const uint64_t adesc = make_desc(sbase + F_OFF_HS + hb * F_HS_BYTES, 1024, kSw128);
@@ -294,33 +292,37 @@ __global__ void __launch_bounds__(F_THREADS, 1) tc_mlp_kernel(const __grid_const
       }
     }
   } else if (warp >= 4 && warp < 12) {
-    // ---- GELU warps ----
-    const int quarter = warp & 3, half = (warp - 4) >> 2;
+    // ---- GELU warps: two groups of four; group = parity of the chunk, so that the fixed costs of a
+    // chunk (barrier wake-up, TMEM load, proxy fence: ~700 cycles) of one group hide under the
+    // arithmetic of the other.  Thread = token row, all 64 hidden columns of the chunk. ----
+    const int grp = (warp - 4) >> 2, quarter = warp & 3;
     const int r = quarter * 32 + lane;
-    const uint32_t trow = tmem + F_TM_H + ((uint32_t)(quarter * 32) << 16) + half * 32;
-    const uint32_t hs_row = smem_u32(smem) + F_OFF_HS + r * 128;
+    const int hb = grp;
+    const uint32_t trow = tmem + F_TM_H + hb * F_CH + ((uint32_t)(quarter * 32) << 16);
+    const uint32_t dst = smem_u32(smem) + F_OFF_HS + hb * F_HS_BYTES + r * 128;
     const int rsw = r & 7;
-    uint32_t v[32];
-    for (int g = 0; g < G; ++g) {
-      const int hb = g & 1;
+    uint32_t v0[32], v1[32];
+    for (int g = grp; g < G; g += 2) {
       const uint32_t ph = (g >> 1) & 1;
       mbar_wait(&h_full[hb], ph);
       tc_fence_after();
-      tmem_ld32(trow + hb * F_CH, v);
+      tmem_ld32(trow, v0);
+      tmem_ld32(trow + 32, v1);
       tmem_ld_wait();
       tc_fence_before();
-      mbar_arrive(&h_free[hb]);
-      uint32_t pk[16];
+      mbar_arrive_warp(&h_free[hb]);
+      uint32_t pk[32];
 #pragma unroll
-      for (int i = 0; i < 16; ++i) pk[i] = gelu2_bf16(__uint_as_float(v[2 * i]), __uint_as_float(v[2 * i + 1]));
+      for (int i = 0; i < 16; ++i) pk[i] = gelu2_bf16(__uint_as_float(v0[2 * i]), __uint_as_float(v0[2 * i + 1]));
+#pragma unroll
+      for (int i = 0; i < 16; ++i) pk[16 + i] = gelu2_bf16(__uint_as_float(v1[2 * i]), __uint_as_float(v1[2 * i + 1]));
       mbar_wait(&hs_empty[hb], ph ^ 1);          // GEMM2 of chunk g-2 has released this buffer
-      // 32 hidden columns = 64 B = chunks [half*4, half*4+4) of this row's 128 B, XOR-swizzled
-      const uint32_t dst = hs_row + hb * F_HS_BYTES;
+      // 64 hidden columns = the row's 128 B = eight 16-byte pieces, XOR-swizzled
 #pragma unroll
-      for (int q = 0; q < 4; ++q)
-        st_shared_v4(dst + (((half * 4 + q) ^ rsw) << 4), pk[4 * q], pk[4 * q + 1], pk[4 * q + 2], pk[4 * q + 3]);
+      for (int q = 0; q < 8; ++q)
+        st_shared_v4(dst + ((q ^ rsw) << 4), pk[4 * q], pk[4 * q + 1], pk[4 * q + 2], pk[4 * q + 3]);
       fence_proxy_async();
-      mbar_arrive(&hs_full[hb]);
+      mbar_arrive_warp(&hs_full[hb]);
     }
   } else if (warp >= 12) {
     // ---- epilogue warps: state = LN(state + acc), fp32 state and bf16 shadow; thread = row ----
@@ -351,7 +353,7 @@ __global__ void __launch_bounds__(F_THREADS, 1) tc_mlp_kernel(const __grid_const
 #pragma unroll
         for (int k = 0; k < 8; ++k) rr[k] = lds128(rrow + ((k ^ rsw) << 4));
         tmem_ld_wait();
-        if (c < F_R_SLOTS) mbar_arrive(&r_empty[slot]);
+        if (c < F_R_SLOTS) mbar_arrive_warp(&r_empty[slot]);
 #pragma unroll
         for (int k = 0; k < 8; ++k) {
           const float a0 = __uint_as_float(v[4 * k]) + rr[k].x, a1 = __uint_as_float(v[4 * k + 1]) + rr[k].y,
@@ -399,12 +401,12 @@ __global__ void __launch_bounds__(F_THREADS, 1) tc_mlp_kernel(const __grid_const
         }
       }
       tc_fence_before();
-      mbar_arrive(&out_empty[ob]);
+      mbar_arrive_warp(&out_empty[ob]);
       // the staging memory goes back to the residual producer once the last stores have read it
       if (store_leader) bulk_wait_read0();
       epi_bar();
 #pragma unroll
-      for (int s = 0; s < F_R_SLOTS; ++s) mbar_arrive(&r_empty[s]);
+      for (int s = 0; s < F_R_SLOTS; ++s) mbar_arrive_warp(&r_empty[s]);
     }
     if (store_leader) bulk_wait0();       // shared memory must outlive the last bulk stores
   }

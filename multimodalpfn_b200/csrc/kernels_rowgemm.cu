@@ -74,9 +74,9 @@ __global__ void __launch_bounds__(R_THREADS, 1) tc_rowgemm_kernel(const __grid_c
   uint64_t* a_full = bars + 1;         // A tile landed
   uint64_t* a_empty = bars + 3;        // ... and its MMAs have completed
   uint64_t* acc_full = bars + 5;       // [2] accumulator complete in TMEM
-  uint64_t* acc_empty = bars + 7;      // [2] ... and drained by the epilogue (128 arrivals)
+  uint64_t* acc_empty = bars + 7;      // [2] ... and drained by the epilogue (one arrival per warp: 4)
   uint64_t* r_full = bars + 9;         // [3] residual chunk landed
-  uint64_t* r_empty = bars + 12;       // [3] ... and consumed (128 arrivals)
+  uint64_t* r_empty = bars + 12;       // [3] ... and consumed (one arrival per warp: 4)
   uint32_t* tmem_slot = (uint32_t*)(bars + 15);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -94,11 +94,11 @@ __global__ void __launch_bounds__(R_THREADS, 1) tc_rowgemm_kernel(const __grid_c
     mbar_init(a_empty, 1);
     for (int s = 0; s < 2; ++s) {
       mbar_init(&acc_full[s], 1);
-      mbar_init(&acc_empty[s], 128);
+      mbar_init(&acc_empty[s], 4);
     }
     for (int s = 0; s < R_R_SLOTS; ++s) {
       mbar_init(&r_full[s], 1);
-      mbar_init(&r_empty[s], 128);
+      mbar_init(&r_empty[s], 4);
     }
     fence_barrier_init();
   }
@@ -224,7 +224,7 @@ __global__ void __launch_bounds__(R_THREADS, 1) tc_rowgemm_kernel(const __grid_c
 #pragma unroll
           for (int k = 0; k < 8; ++k) rr[k] = lds128(rrow + ((k ^ rsw) << 4));
           tmem_ld_wait();
-          mbar_arrive(&r_empty[slot]);
+          mbar_arrive_warp(&r_empty[slot]);
 #pragma unroll
           for (int k = 0; k < 8; ++k) {
             const float a0 = __uint_as_float(v[4 * k]) + rr[k].x, a1 = __uint_as_float(v[4 * k + 1]) + rr[k].y,
@@ -312,7 +312,7 @@ __global__ void __launch_bounds__(R_THREADS, 1) tc_rowgemm_kernel(const __grid_c
         }
       }
       tc_fence_before();
-      mbar_arrive(&acc_empty[ab]);
+      mbar_arrive_warp(&acc_empty[ab]);
     }
     if (store_leader) bulk_wait0();       // shared memory must outlive the last bulk stores
   }

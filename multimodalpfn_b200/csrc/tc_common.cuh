@@ -26,6 +26,13 @@ __device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
 __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
+// One arrival per WARP: the lanes synchronise (which also orders their prior shared-memory / TMEM
+// accesses before lane 0's release-arrive) and lane 0 arrives.  128 threads arriving one by one are
+// 128 serialised atomics on one shared-memory word — several hundred cycles per hand-off.
+__device__ __forceinline__ void mbar_arrive_warp(uint64_t* bar) {
+  __syncwarp();
+  if ((threadIdx.x & 31) == 0) mbar_arrive(bar);
+}
 __device__ __noinline__ void mbar_timeout() {
   printf("mmpfn: mbarrier timeout (block %d,%d thread %d)\n", blockIdx.x, blockIdx.y, threadIdx.x);
   __trap();
@@ -68,6 +75,32 @@ __device__ __forceinline__ bool elect_one() {
   uint32_t pred;
   asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(pred));
   return pred != 0;
+}
+// Wait for two barriers at once.  Even a wait that is already satisfied costs the calling thread
+// ~200-250 cycles (SYNCS round trip): a single-thread issue loop that checks two barriers per step
+// pays it once instead of twice when both probes are in flight together.
+__device__ __forceinline__ void mbar_wait2(uint64_t* bar_a, uint32_t parity_a, uint64_t* bar_b, uint32_t parity_b) {
+  const uint32_t a = smem_u32(bar_a), b = smem_u32(bar_b);
+  uint32_t n = 0;
+  long long t0 = 0;
+  while (true) {
+    uint32_t da, db;
+    asm volatile(
+        "{\n\t.reg .pred p, q;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%2], %3, %6;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 q, [%4], %5, %6;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t"
+        "selp.u32 %1, 1, 0, q;\n\t}"
+        : "=r"(da), "=r"(db)
+        : "r"(a), "r"(parity_a), "r"(b), "r"(parity_b), "r"(20000u)
+        : "memory");
+    if (da & db) return;
+    if ((++n & 4095u) == 0) {
+      const long long now = clock64();
+      if (t0 == 0) t0 = now;
+      else if (now - t0 > 4000000000LL) mbar_timeout();
+    }
+  }
 }
 __device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
