@@ -246,7 +246,7 @@ __global__ void __launch_bounds__(A_THREADS, AttnCfg<BK>::kMinCtas)
     // maximum when that has grown by more than kTau (log2 units): p = 2^((s - m_ref) c) then stays
     // below 2^kTau, which fp32 sums and bf16 P hold without loss, and the round trip that rescales O
     // in TMEM (needed on nearly every tile otherwise) becomes rare after the first tiles.
-    constexpr float kTau = 8.0f;
+    constexpr float kSumLimit = 256.0f;          // 2^kTau, kTau = 8
     constexpr int kNP = BK / 2;                  // pairs of keys per row and tile
     constexpr int kAhead = 4;                    // pairs whose scaled argument is ready ahead of their ex2
     constexpr int kBehind = 5;                   // pairs whose ex2 is in flight before the first consumer reads one
@@ -272,24 +272,17 @@ __global__ void __launch_bounds__(A_THREADS, AttnCfg<BK>::kMinCtas)
         }
       };
       // One software-pipelined sweep over the row, written so that a lone warp keeps the MUFU pipe fed:
-      // step k scales pair k+kAhead (FFMA2, and folds it into the row maximum, FMNMX3), starts the two
-      // ex2 of pair k, and retires pair k-kBehind (row sum FADD2, bf16 pack F2FP, every fourth pair a
-      // 16-byte store into the 128B-swizzled A tile of the PV MMA: 8 keys = one chunk of the row's
-      // 128 B k-block line, chunk index XOR (row & 7)).  Values are transformed in place: s -> x -> p.
-      float mxa, mxb;
+      // step k scales pair k+kAhead (FFMA2), starts the two ex2 of pair k, and retires pair k-kBehind
+      // (row sum FADD2, bf16 pack F2FP, every fourth pair a 16-byte store into the 128B-swizzled A
+      // tile of the PV MMA: 8 keys = one chunk of the row's 128 B k-block line, chunk index XOR
+      // (row & 7)).  Values are transformed in place: s -> x -> p.  No row maximum is tracked here.
       const uint64_t c2 = pack_f32x2(c, c);
       auto sweep = [&](float mc) -> float {
         const uint64_t nmc2 = pack_f32x2(-mc, -mc);
         uint64_t lsum2 = 0ull;                                // (0.f, 0.f)
         uint32_t pk[4];
-        mxa = -INFINITY;
-        mxb = -INFINITY;
         auto scale = [&](int k) {
           const float sa = __uint_as_float(sv[2 * k]), sb2 = __uint_as_float(sv[2 * k + 1]);
-          if (!(DBG & 32)) {
-            if (k & 1) mxb = fmaxf(mxb, fmaxf(sa, sb2));
-            else mxa = fmaxf(mxa, fmaxf(sa, sb2));
-          }
           float xa, xb;
           unpack_f32x2(fma_f32x2(pack_f32x2(sa, sb2), c2, nmc2), xa, xb);
           sv[2 * k] = __float_as_uint(xa);
@@ -325,10 +318,8 @@ __global__ void __launch_bounds__(A_THREADS, AttnCfg<BK>::kMinCtas)
         unpack_f32x2(lsum2, lsum0, lsum1);
         return lsum0 + lsum1;
       };
-      if (!(DBG & 2)) load_row();
-      if (threadIdx.x == 0) ATTN_TRACE(j * 8 + 2);
-      if (j == 0) {
-        // first tile: the reference is the true maximum of the tile
+      // the true maximum of the row of S held in sv (first tile, and the rare repeat below)
+      auto row_max = [&]() -> float {
         float mx0 = -INFINITY, mx1 = -INFINITY, mx2 = -INFINITY, mx3 = -INFINITY;
 #pragma unroll
         for (int i = 0; i < BK; i += 8) {
@@ -337,25 +328,30 @@ __global__ void __launch_bounds__(A_THREADS, AttnCfg<BK>::kMinCtas)
           mx2 = fmaxf(mx2, fmaxf(__uint_as_float(sv[i + 4]), __uint_as_float(sv[i + 5])));
           mx3 = fmaxf(mx3, fmaxf(__uint_as_float(sv[i + 6]), __uint_as_float(sv[i + 7])));
         }
-        m_ref = fmaxf(fmaxf(mx0, mx1), fmaxf(mx2, mx3));
-      }
+        return fmaxf(fmaxf(mx0, mx1), fmaxf(mx2, mx3));
+      };
+      if (!(DBG & 2)) load_row();
+      if (threadIdx.x == 0) ATTN_TRACE(j * 8 + 2);
+      if (j == 0) m_ref = row_max();             // first tile: the reference is the true maximum of the tile
       if (threadIdx.x == 0) ATTN_TRACE(j * 8 + 3);
-      // later tiles: exponentials are taken against the reference of the previous tile while the
-      // maximum is still being found; only when a row's maximum then turns out to have grown by more
-      // than kTau is the sweep repeated (rare: the running maximum of n keys moves ~ log n times).
-      // S was consumed in place, so the repeat reads it from TMEM again: the S columns are handed
-      // back to the MMA warp only after the decision (S is double buffered: no one is waiting).
+      // Later tiles: exponentials are taken against the reference of the earlier tiles, and no maximum
+      // is computed at all: a score more than kTau (log2 units) above the reference shows up as a row
+      // sum above 2^kTau (p <= sum p; inf and NaN fail the comparison too).  Only then — rare: the
+      // running maximum of n keys moves ~ log n times, and a sum that merely crowds the limit just
+      // refreshes the reference — is the true maximum taken and the sweep repeated.  S was consumed in
+      // place, so the repeat reads it from TMEM again: the S columns are handed back to the MMA warp
+      // only after the decision (S is double buffered: no one is waiting).
       float lsum = sweep(m_ref * c);
-      const float mx = fmaxf(mxa, mxb);
-      const bool moved = (mx - m_ref) * c > kTau;
+      const bool moved = !(lsum <= kSumLimit) && !(DBG & 32);
       const bool any_moved = __any_sync(0xffffffffu, moved);   // tcgen05.ld is warp-collective
       float alpha = 1.0f;
       if (any_moved) {
+        load_row();
         if (moved) {
+          const float mx = fmaxf(row_max(), m_ref);
           alpha = fast_exp2((m_ref - mx) * c);
           m_ref = mx;
         }
-        load_row();
         lsum = sweep(m_ref * c);
       }
       tc_fence_before();

@@ -201,9 +201,12 @@ __device__ __forceinline__ float fast_exp2(float x) {
 
 // 2^x on the FMA/ALU pipes (no MUFU): x = n + f with n = round(x), f in [-0.5, 0.5]; 2^f by a
 // degree-3 minimax polynomial (max relative error 7.6e-5, far below the bf16 rounding of P), the
-// integer part spliced into the exponent field.  x is clamped at -126 (result ~1e-38 ~ 0).
+// integer part spliced into the exponent field.  x is clamped to [-126, 126]: below, the result is
+// ~1e-38 ~ 0; above, it saturates at ~2^126 instead of wrapping the exponent into the sign bit (the
+// item attention detects scores far above its reference by the row sum: that must come out huge,
+// never negative).
 __device__ __forceinline__ float poly_exp2(float x) {
-  x = fmaxf(x, -126.0f);
+  x = fminf(fmaxf(x, -126.0f), 126.0f);
   const float r = x + 12582912.0f;            // 1.5 * 2^23: round(x) lands in the low mantissa bits
   const float f = x - (r - 12582912.0f);
   float p = fmaf(0.05520550534129143f, f, 0.24261397123336792f);

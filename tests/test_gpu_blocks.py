@@ -117,6 +117,38 @@ def test_out_projection_layernorm_tcgen05(M):
     assert e1 < 2e-4 and e2 < 0.03, (e1, e2)        # fp32 accumulation; bf16 rounding of O(4) values
 
 
+@pytest.mark.parametrize("n_q,n_kv,shared,scale", [(128, 48, 0, 1.0), (333, 1999, 0, 1.0), (300, 2000, 1, 1.0),
+                                                   (257, 1000, 0, 4.0), (200, 1500, 1, 8.0), (130, 700, 0, 16.0),
+                                                   (1, 1, 0, 1.0), (5, 49, 1, 2.0)])
+def test_item_attention_tcgen05(n_q, n_kv, shared, scale):
+    """softmax(q k^T / sqrt 32) v across items (layer.py:341-379) on tcgen05 vs torch fp32 on the same bf16
+    operands; ragged sizes, the shared head-0 K/V of the test pass (multi_head_attention.py:436-445), and
+    score scales at which the running maximum moves often and exponentials overflow against a stale
+    reference (scale 16: |score| ~ 1000)."""
+    lib = _lib.load()
+    B, T = 2, 3
+    planes, kv_planes = B * T * 6, (B * T if shared else B * T * 6)
+    qpad, kpad = (n_q + 63) // 64 * 64, (n_kv + 63) // 64 * 64
+    g = torch.Generator().manual_seed(n_q * 31 + n_kv)
+    q = (torch.randn(planes, qpad, 32, generator=g) * scale).cuda().to(torch.bfloat16)
+    k = (torch.randn(kv_planes, kpad, 32, generator=g) * scale).cuda().to(torch.bfloat16)
+    vt = torch.randn(kv_planes, 32, kpad, generator=g).cuda().to(torch.bfloat16)
+    out = torch.full((B, n_q, T, 192), float("nan"), dtype=torch.bfloat16, device="cuda")
+    _lib.check(lib.mmpfn_item_attention_bf16(q.data_ptr(), k.data_ptr(), vt.data_ptr(), B, T, n_q, qpad, n_kv, kpad,
+                                             shared, out.data_ptr(), _stream()), "item_attention")
+    torch.cuda.synchronize()
+    assert not torch.isnan(out.float()).any()
+    err = 0.0
+    for plane in range(planes):
+        bt, h = divmod(plane, 6)
+        b, t = divmod(bt, T)
+        kp = bt if shared else plane
+        ref = torch.softmax(q[plane, :n_q].float() @ k[kp, :n_kv].float().T / 32 ** 0.5, dim=-1) @ vt[kp, :, :n_kv].float().T
+        err = max(err, float((out[b, :, t, h * 32:(h + 1) * 32].float() - ref).abs().max()))
+    # P is rounded to bf16 (2^-9 relative) before P V, the output to bf16: O(1) values -> ~1e-2 worst case
+    assert err < 0.03, err
+
+
 def _one_layer_model(precision, seed=3):
     from multimodalpfn_b200.model import B200PerFeatureTransformer
     geom = Geometry(nlayers=1, mgm_heads=2, cap_heads=4)
