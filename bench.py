@@ -401,6 +401,16 @@ def kernel_breakdown(torch, _lib, dev, S, T, B, peaks):
         lib.mmpfn_linear_bf16(A.data_ptr(), W.data_ptr(), M, 3 * E, E, 0, O.data_ptr(), st), "qkv"))
     res["qkv_proj"] = entry(ms, 2.0 * M * 3 * E * E, 2.0 * (M * E + 3 * E * E + M * 3 * E), M=M, N=3 * E, K=E)
     del O
+    # item-attention QKV projection + scatter into q/k/v^T planes (+ head-0 context): [B][S][T] tiles by 4-D TMA
+    Sp = (S + 63) // 64 * 64
+    P = B * T * NH
+    qkv = [torch.empty(P * Sp * DK, device=dev, dtype=torch.bfloat16) for _ in range(3)]
+    ctx = [torch.empty(B * T * Sp * DK, device=dev, dtype=torch.bfloat16) for _ in range(2)]
+    ms = _time_kernel(torch, lambda: _lib.check(
+        lib.mmpfn_item_qkv_bf16(A.data_ptr(), W.data_ptr(), B, S, T, Sp, 3, qkv[0].data_ptr(), qkv[1].data_ptr(),
+                                qkv[2].data_ptr(), ctx[0].data_ptr(), ctx[1].data_ptr(), st), "item_qkv"))
+    res["item_qkv_scatter"] = entry(ms, 2.0 * M * 3 * E * E, 2.0 * (M * E + 3 * E * E + M * 3 * E + 2 * B * T * S * DK), M=M)
+    del qkv, ctx
     # attention output projection + residual + LayerNorm: state fp32 in/out, bf16 shadow out
     x = torch.randn(M, E, device=dev, generator=g)
     xb = torch.empty(M, E, device=dev, dtype=torch.bfloat16)

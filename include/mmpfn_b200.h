@@ -187,6 +187,14 @@ int mmpfn_linear_bf16(const uint16_t* A, const uint16_t* W, int M, int N, int K,
 int mmpfn_linear_ln_bf16(const uint16_t* A, const uint16_t* W, int M, float* state_f32, uint16_t* state_bf16,
                          void* stream);
 
+/* The QKV projection of the attention across items (multi_head_attention.py:430-434) with its scatter into
+ * the layouts the item-attention kernel reads: state [B][S][T][192] bf16, w_qkv [n_proj*192][192] bf16
+ * (n_proj = 3: q|k|v, the train pass; 1: q only, the test pass) ->
+ *   q, k [B*T*nhead][S_pad][32],  vt [B*T*nhead][32][S_pad],  and, when given, the head-0 context
+ *   k0 [B*T][S_pad][32], vt0 [B*T][32][S_pad] (multi_head_attention.py:328-336).  S_pad % 64 == 0. */
+int mmpfn_item_qkv_bf16(const uint16_t* state_bf16, const uint16_t* w_qkv, int B, int S, int T, int S_pad, int n_proj,
+                        uint16_t* q, uint16_t* k, uint16_t* vt, uint16_t* k0, uint16_t* vt0, void* stream);
+
 /* The MLP sublayer alone (mlp.py:93-138 + layer.py:437-455), one fused tcgen05 kernel, in place:
  *   state_f32 [M][192] <- LayerNorm(state_f32 + W2 gelu(W1 state_bf16)),  state_bf16 <- bf16(state_f32)
  * w1 [768][192], w2 [192][768] bf16 (the reference's linear1.weight / linear2.weight). */

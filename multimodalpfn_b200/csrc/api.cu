@@ -538,6 +538,20 @@ int mmpfn_linear_ln_bf16(const uint16_t* A, const uint16_t* W, int M, float* sta
   return proj_gemm(o, (cudaStream_t)stream);
 }
 
+int mmpfn_item_qkv_bf16(const uint16_t* state_bf16, const uint16_t* w_qkv, int B, int S, int T, int S_pad, int n_proj,
+                        uint16_t* q, uint16_t* k, uint16_t* vt, uint16_t* k0, uint16_t* vt0, void* stream) {
+  MMPFN_TRY(require_device());
+  if (!state_bf16 || !w_qkv || !q || B < 1 || S < 1 || T < 1 || S_pad < S || S_pad % 64 || (n_proj != 1 && n_proj != 3) ||
+      (n_proj == 3 && (!k || !vt))) {
+    set_error("item_qkv_bf16: bad arguments");
+    return MMPFN_EINVAL;
+  }
+  TcGemm g{};
+  g.A = state_bf16; g.W = w_qkv; g.N = n_proj * kE; g.K = kE; g.items = 1; g.B = B; g.S = S; g.T = T;
+  g.epi = TC_EPI_QKV_ITEMS; g.q_out = q; g.k_out = k; g.vt_out = vt; g.k0_out = k0; g.vt0_out = vt0; g.S_pad = S_pad;
+  return proj_gemm(g, (cudaStream_t)stream);
+}
+
 int mmpfn_mlp_bf16(float* state_f32, uint16_t* state_bf16, const uint16_t* w1, const uint16_t* w2, int M,
                    void* stream) {
   MMPFN_TRY(require_device());

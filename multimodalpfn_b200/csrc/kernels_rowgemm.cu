@@ -61,18 +61,31 @@ struct RowGemmArgs {
   int S_pad;
 };
 
+// destinations of the item-attention QKV scatter (TC_EPI_QKV_ITEMS): q/k planes [plane][S][32] (row pitch
+// 64 B), v^T planes [plane][32][S], and the head-0 context copies (planes = (b, t))
+struct alignas(64) ItemMaps {
+  CUtensorMap q, k, vt, k0, vt0;
+};
+
 template <int EPI>
 __global__ void __launch_bounds__(R_THREADS, 1) tc_rowgemm_kernel(const __grid_constant__ CUtensorMap map_a,
                                                                   const __grid_constant__ CUtensorMap map_w,
                                                                   const __grid_constant__ CUtensorMap map_r,
                                                                   const __grid_constant__ CUtensorMap map_y,
+                                                                  const __grid_constant__ ItemMaps im,
                                                                   const RowGemmArgs p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
   uint64_t* bars = (uint64_t*)(smem + R_OFF_BAR);
   uint64_t* w_full = bars;             // W tile landed (once)
-  uint64_t* a_full = bars + 1;         // A tile landed
-  uint64_t* a_empty = bars + 3;        // ... and its MMAs have completed
+  uint64_t* a_full = bars + 1;         // [kAStages] A tile landed
+  uint64_t* a_empty = bars + 3;        // [kAStages] ... and its MMAs have completed
+  // The LayerNorm variant is HBM bound at ~7 us per tile and needs the shared memory for the residual
+  // ring: one A buffer.  The plain projections move a third of the bytes per tile: there the load of
+  // tile i+1 must not wait for the MMAs of tile i, and the second A buffer takes the ring's place.
+  constexpr int kAStages = EPI == TC_EPI_RESID_LN ? 1 : 2;
+  static_assert(R_R_SLOTS * R_R_BYTES == R_A_BYTES, "the second A buffer aliases the residual ring");
+  static_assert(kH * R_BM * 64 == 2 * R_Y32_BYTES + 2 * R_Y16_BYTES, "six staged heads fill the staging area");
   uint64_t* acc_full = bars + 5;       // [2] accumulator complete in TMEM
   uint64_t* acc_empty = bars + 7;      // [2] ... and drained by the epilogue (one arrival per warp: 4)
   uint64_t* r_full = bars + 9;         // [3] residual chunk landed
@@ -89,9 +102,16 @@ __global__ void __launch_bounds__(R_THREADS, 1) tc_rowgemm_kernel(const __grid_c
     prefetch_tmap(&map_w);
     if (EPI == TC_EPI_RESID_LN) prefetch_tmap(&map_r);
     if (EPI != TC_EPI_QKV_ITEMS) prefetch_tmap(&map_y);
+    if (EPI == TC_EPI_QKV_ITEMS) {
+      prefetch_tmap(&im.q);
+      prefetch_tmap(&im.k);
+      prefetch_tmap(&im.vt);
+    }
     mbar_init(w_full, 1);
-    mbar_init(a_full, 1);
-    mbar_init(a_empty, 1);
+    for (int s = 0; s < kAStages; ++s) {
+      mbar_init(&a_full[s], 1);
+      mbar_init(&a_empty[s], 1);
+    }
     for (int s = 0; s < 2; ++s) {
       mbar_init(&acc_full[s], 1);
       mbar_init(&acc_empty[s], 4);
@@ -118,23 +138,25 @@ __global__ void __launch_bounds__(R_THREADS, 1) tc_rowgemm_kernel(const __grid_c
       for (int kb = 0; kb < 3; ++kb) tma_load_2d(smem + R_OFF_W + kb * (R_BN * 128), &map_w, w_full, kb * 64, jn * R_BN);
       auto load_a = [&](int i) {
         const int mt = tile_of(i);
-        mbar_wait(a_empty, (i & 1) ^ 1);
-        mbar_expect_tx(a_full, R_A_BYTES);
-        uint8_t* dst = smem + R_OFF_A;
+        const int as = i % kAStages;
+        uint64_t* full = &a_full[as];
+        mbar_wait(&a_empty[as], ((i / kAStages) & 1) ^ 1);
+        mbar_expect_tx(full, R_A_BYTES);
+        uint8_t* dst = smem + R_OFF_A + as * R_A_BYTES;
         if (p.items) {
           const int per_b = p.T * p.tiles_s;
           const int tb = mt / per_b, r = mt % per_b;
           const int tt = r / p.tiles_s, s0 = (r % p.tiles_s) * R_BM;
 #pragma unroll
-          for (int kb = 0; kb < 3; ++kb) tma_load_4d(dst + kb * (R_BM * 128), &map_a, a_full, kb * 64, tt, s0, tb);
+          for (int kb = 0; kb < 3; ++kb) tma_load_4d(dst + kb * (R_BM * 128), &map_a, full, kb * 64, tt, s0, tb);
         } else {
 #pragma unroll
-          for (int kb = 0; kb < 3; ++kb) tma_load_2d(dst + kb * (R_BM * 128), &map_a, a_full, kb * 64, mt * R_BM);
+          for (int kb = 0; kb < 3; ++kb) tma_load_2d(dst + kb * (R_BM * 128), &map_a, full, kb * 64, mt * R_BM);
         }
       };
       if (my_tiles > 0) load_a(0);
       for (int i = 0; i < my_tiles; ++i) {
-        if (i + 1 < my_tiles) load_a(i + 1);
+        if (i + 1 < my_tiles) load_a(i + 1);      // blocks until its buffer's previous MMAs have completed
         if (EPI == TC_EPI_RESID_LN) {
           const int m0 = tile_of(i) * R_BM;
           for (int c = 0; c < R_NCH; ++c) {
@@ -155,18 +177,19 @@ __global__ void __launch_bounds__(R_THREADS, 1) tc_rowgemm_kernel(const __grid_c
       for (int i = 0; i < my_tiles; ++i) {
         const int ab = i & 1;
         const uint32_t ph = (i >> 1) & 1;
-        mbar_wait(a_full, i & 1);
+        const int as = i % kAStages;
+        mbar_wait(&a_full[as], (i / kAStages) & 1);
         mbar_wait(&acc_empty[ab], ph ^ 1);
         tc_fence_after();
 #pragma unroll
         for (int kb = 0; kb < 3; ++kb) {
-          const uint64_t adesc = make_desc(sbase + R_OFF_A + kb * (R_BM * 128), 1024, kSw128);
+          const uint64_t adesc = make_desc(sbase + R_OFF_A + as * R_A_BYTES + kb * (R_BM * 128), 1024, kSw128);
           const uint64_t bdesc = make_desc(sbase + R_OFF_W + kb * (R_BN * 128), 1024, kSw128);
 #pragma unroll
           for (int k = 0; k < 4; ++k)
             umma_bf16(tmem + ab * R_BN, adesc + (uint64_t)(k * 2), bdesc + (uint64_t)(k * 2), idesc, (kb | k) != 0);
         }
-        umma_commit(a_empty);
+        umma_commit(&a_empty[as]);
         umma_commit(&acc_full[ab]);
       }
     }
@@ -271,44 +294,66 @@ __global__ void __launch_bounds__(R_THREADS, 1) tc_rowgemm_kernel(const __grid_c
           }
         }
       } else {  // TC_EPI_QKV_ITEMS: n-tile jn in {q,k,v}; 32-column chunk = head
+        // Every head's [128 rows x 32] block goes through an 8 KB staging block and out by TMA: q and k
+        // as [128][64 B] rows (64B swizzle) into their plane, v transposed ([32 d][128 s], two 128B-
+        // swizzled 64-column blocks) so that P V is a K-major x K-major MMA.  Rows past S are clipped by
+        // the tensor maps.  Head 0 of k and v is stored a second time into the layer's context.
         const int per_b = p.T * p.tiles_s;
         const int tb = mt / per_b, rem = mt % per_b;
         const int tt = rem / p.tiles_s, s0 = (rem % p.tiles_s) * R_BM;
-        const int s = s0 + r;
-        const bool ok = s < p.S;
-        const long long bt = (long long)tb * p.T + tt;
+        const int bt = tb * p.T + tt;
+        // all six heads are staged (6 x 8 KB = the whole staging area) before one fence, one barrier
+        // and one group of stores per tile; the stores of the previous tile must have read it first
+        if (store_leader) bulk_wait_read0();
+        epi_bar();
 #pragma unroll 1
         for (int h = 0; h < kH; ++h) {
+          const uint32_t slot = smem_u32(smem) + R_OFF_Y32 + h * (R_BM * 64);
           tmem_ld32(trow + h * 32, v);
           tmem_ld_wait();
-          if (!ok) continue;
-          const long long plane = bt * kH + h;
           if (jn < 2) {
-            uint32_t pk[16];
+            const uint32_t yrow = slot + r * 64;
 #pragma unroll
-            for (int k = 0; k < 16; ++k) pk[k] = pack_bf16x2(__uint_as_float(v[2 * k]), __uint_as_float(v[2 * k + 1]));
-            uint16_t* dst = (jn == 0 ? p.q_out : p.k_out) + (plane * p.S_pad + s) * kD;
-            uint4* d4 = reinterpret_cast<uint4*>(dst);
-#pragma unroll
-            for (int k = 0; k < 4; ++k) d4[k] = make_uint4(pk[4 * k], pk[4 * k + 1], pk[4 * k + 2], pk[4 * k + 3]);
-            if (jn == 1 && h == 0 && p.k0_out) {
-              uint4* c4 = reinterpret_cast<uint4*>(p.k0_out + (bt * p.S_pad + s) * kD);
-#pragma unroll
-              for (int k = 0; k < 4; ++k) c4[k] = make_uint4(pk[4 * k], pk[4 * k + 1], pk[4 * k + 2], pk[4 * k + 3]);
-            }
+            for (int k = 0; k < 4; ++k)
+              st_shared_v4(yrow + ((k ^ ((r >> 1) & 3)) << 4),
+                           pack_bf16x2(__uint_as_float(v[8 * k]), __uint_as_float(v[8 * k + 1])),
+                           pack_bf16x2(__uint_as_float(v[8 * k + 2]), __uint_as_float(v[8 * k + 3])),
+                           pack_bf16x2(__uint_as_float(v[8 * k + 4]), __uint_as_float(v[8 * k + 5])),
+                           pack_bf16x2(__uint_as_float(v[8 * k + 6]), __uint_as_float(v[8 * k + 7])));
           } else {
-            // V is stored transposed ([d][s]) so that P V is a K-major x K-major MMA; consecutive
-            // lanes hold consecutive s -> 64 B coalesced per d
-            uint16_t* dst = p.vt_out + plane * kD * p.S_pad + s;
-            uint16_t* dst0 = (h == 0 && p.vt0_out) ? p.vt0_out + bt * kD * p.S_pad + s : nullptr;
+            // element (d, s = r): 64-column block r / 64, row d (128 B), 16-byte piece ((r % 64) / 8) ^ (d & 7)
+            const uint32_t base = slot + (r >> 6) * (kD * 128) + ((r & 7) << 1);
+            const int ch = (r & 63) >> 3;
 #pragma unroll
             for (int d = 0; d < kD; ++d) {
               __nv_bfloat16 bv = __float2bfloat16_rn(__uint_as_float(v[d]));
-              const uint16_t bits = *reinterpret_cast<uint16_t*>(&bv);
-              dst[(long long)d * p.S_pad] = bits;
-              if (dst0) dst0[(long long)d * p.S_pad] = bits;
+              st_shared_u16(base + d * 128 + ((ch ^ (d & 7)) << 4), *reinterpret_cast<uint16_t*>(&bv));
             }
           }
+        }
+        fence_proxy_async();
+        epi_bar();
+        if (store_leader) {
+#pragma unroll 1
+          for (int h = 0; h < kH; ++h) {
+            const uint8_t* slot = smem + R_OFF_Y32 + h * (R_BM * 64);
+            const int plane = bt * kH + h;
+            if (jn == 0) {
+              tma_store_3d(&im.q, slot, 0, s0, plane);
+            } else if (jn == 1) {
+              tma_store_3d(&im.k, slot, 0, s0, plane);
+              if (h == 0 && p.k0_out) tma_store_3d(&im.k0, slot, 0, s0, bt);
+            } else {
+#pragma unroll
+              for (int kb = 0; kb < 2; ++kb) {
+                if (s0 + kb * 64 < p.S) {
+                  tma_store_3d(&im.vt, slot + kb * (kD * 128), s0 + kb * 64, 0, plane);
+                  if (h == 0 && p.vt0_out) tma_store_3d(&im.vt0, slot + kb * (kD * 128), s0 + kb * 64, 0, bt);
+                }
+              }
+            }
+          }
+          bulk_commit();
         }
       }
       tc_fence_before();
@@ -326,13 +371,13 @@ __global__ void __launch_bounds__(R_THREADS, 1) tc_rowgemm_kernel(const __grid_c
 
 template <int EPI>
 int launch_rowgemm_t(const CUtensorMap& ma, const CUtensorMap& mw, const CUtensorMap& mr, const CUtensorMap& my,
-                     const RowGemmArgs& a, int grid, cudaStream_t st) {
+                     const ItemMaps& im, const RowGemmArgs& a, int grid, cudaStream_t st) {
   static bool configured = false;
   if (!configured) {
     cudaFuncSetAttribute(tc_rowgemm_kernel<EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, R_SMEM);
     configured = true;
   }
-  tc_rowgemm_kernel<EPI><<<grid, R_THREADS, R_SMEM, st>>>(ma, mw, mr, my, a);
+  tc_rowgemm_kernel<EPI><<<grid, R_THREADS, R_SMEM, st>>>(ma, mw, mr, my, im, a);
   return count_launch();
 }
 
@@ -395,6 +440,29 @@ int launch_tc_rowgemm(const TcGemm& p, cudaStream_t st) {
     const cuuint32_t box[2] = {R_RC, R_BM};
     MMPFN_TRY(encode_map(&mr, p.resid_f32, 2, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_DATA_TYPE_FLOAT32));
   }
+  ItemMaps im;
+  im.q = im.k = im.vt = im.k0 = im.vt0 = mw;
+  if (p.epi == TC_EPI_QKV_ITEMS) {
+    const cuuint64_t planes = (cuuint64_t)p.B * p.T * kH, planes0 = (cuuint64_t)p.B * p.T;
+    auto rows_map = [&](CUtensorMap* m, const void* base, cuuint64_t np) {      // [plane][S (pitch S_pad)][32]
+      const cuuint64_t dims[3] = {(cuuint64_t)kD, (cuuint64_t)p.S, np};
+      const cuuint64_t strides[2] = {(cuuint64_t)kD * 2, (cuuint64_t)p.S_pad * kD * 2};
+      const cuuint32_t box[3] = {kD, R_BM, 1};
+      return encode_map(m, base, 3, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_64B);
+    };
+    auto cols_map = [&](CUtensorMap* m, const void* base, cuuint64_t np) {      // [plane][32][S (pitch S_pad)]
+      const cuuint64_t dims[3] = {(cuuint64_t)p.S, (cuuint64_t)kD, np};
+      const cuuint64_t strides[2] = {(cuuint64_t)p.S_pad * 2, (cuuint64_t)p.S_pad * kD * 2};
+      const cuuint32_t box[3] = {64, kD, 1};
+      return encode_map(m, base, 3, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_128B);
+    };
+    if (!p.q_out || (a.n_tiles == 3 && (!p.k_out || !p.vt_out))) { set_error("tc_rowgemm: null QKV destination"); return MMPFN_EINVAL; }
+    MMPFN_TRY(rows_map(&im.q, p.q_out, planes));
+    if (p.k_out) MMPFN_TRY(rows_map(&im.k, p.k_out, planes));
+    if (p.vt_out) MMPFN_TRY(cols_map(&im.vt, p.vt_out, planes));
+    if (p.k0_out) MMPFN_TRY(rows_map(&im.k0, p.k0_out, planes0));
+    if (p.vt0_out) MMPFN_TRY(cols_map(&im.vt0, p.vt0_out, planes0));
+  }
   static int n_sm = 0;
   if (!n_sm) {
     int dev = 0;
@@ -407,9 +475,9 @@ int launch_tc_rowgemm(const TcGemm& p, cudaStream_t st) {
   a.ctas_per_n = per_n;
   const int grid = per_n * a.n_tiles;
   switch (p.epi) {
-    case TC_EPI_BF16: return launch_rowgemm_t<TC_EPI_BF16>(ma, mw, mr, my, a, grid, st);
-    case TC_EPI_RESID_LN: return launch_rowgemm_t<TC_EPI_RESID_LN>(ma, mw, mr, my, a, grid, st);
-    case TC_EPI_QKV_ITEMS: return launch_rowgemm_t<TC_EPI_QKV_ITEMS>(ma, mw, mr, my, a, grid, st);
+    case TC_EPI_BF16: return launch_rowgemm_t<TC_EPI_BF16>(ma, mw, mr, my, im, a, grid, st);
+    case TC_EPI_RESID_LN: return launch_rowgemm_t<TC_EPI_RESID_LN>(ma, mw, mr, my, im, a, grid, st);
+    case TC_EPI_QKV_ITEMS: return launch_rowgemm_t<TC_EPI_QKV_ITEMS>(ma, mw, mr, my, im, a, grid, st);
   }
   set_error("tc_rowgemm: unsupported epilogue %d", p.epi);
   return MMPFN_EINVAL;

@@ -149,6 +149,40 @@ def test_item_attention_tcgen05(n_q, n_kv, shared, scale):
     assert err < 0.03, err
 
 
+@pytest.mark.parametrize("B,S,T,n_proj", [(1, 128, 3, 3), (2, 333, 5, 3), (1, 2000, 2, 3), (2, 300, 4, 1), (1, 1, 2, 3)])
+def test_item_qkv_scatter_tcgen05(B, S, T, n_proj):
+    """QKV projection across items + scatter into the attention kernel's plane layouts (q/k row-major,
+    v transposed, head-0 context copies) vs torch on the same bf16 operands."""
+    lib = _lib.load()
+    g = torch.Generator().manual_seed(B * 1000 + S + T)
+    x = torch.randn(B, S, T, 192, generator=g).cuda().to(torch.bfloat16)
+    w = (torch.randn(n_proj * 192, 192, generator=g) / 192 ** 0.5).cuda().to(torch.bfloat16)
+    Sp = (S + 63) // 64 * 64
+    P = B * T * 6
+    q = torch.zeros(P, Sp, 32, dtype=torch.bfloat16, device="cuda")
+    k = torch.zeros(P, Sp, 32, dtype=torch.bfloat16, device="cuda")
+    vt = torch.zeros(P, 32, Sp, dtype=torch.bfloat16, device="cuda")
+    k0 = torch.zeros(B * T, Sp, 32, dtype=torch.bfloat16, device="cuda")
+    vt0 = torch.zeros(B * T, 32, Sp, dtype=torch.bfloat16, device="cuda")
+    full = n_proj == 3
+    _lib.check(lib.mmpfn_item_qkv_bf16(x.data_ptr(), w.data_ptr(), B, S, T, Sp, n_proj, q.data_ptr(),
+                                       k.data_ptr() if full else None, vt.data_ptr() if full else None,
+                                       k0.data_ptr() if full else None, vt0.data_ptr() if full else None, _stream()),
+               "item_qkv")
+    torch.cuda.synchronize()
+    ref = (x.double() @ w.double().T).reshape(B, S, T, n_proj, 6, 32)       # [b, s, t, j, h, d]
+    rq = ref[:, :, :, 0].permute(0, 2, 3, 1, 4).reshape(P, S, 32)             # [(b t h), s, d]
+    assert (q[:, :S].double() - rq).abs().max().item() < 0.04
+    assert (q[:, S:] == 0).all()                                              # rows past S are never written
+    if full:
+        rk = ref[:, :, :, 1].permute(0, 2, 3, 1, 4).reshape(P, S, 32)
+        rv = ref[:, :, :, 2].permute(0, 2, 3, 4, 1).reshape(P, 32, S)         # [(b t h), d, s]
+        assert (k[:, :S].double() - rk).abs().max().item() < 0.04
+        assert (vt[:, :, :S].double() - rv).abs().max().item() < 0.04
+        assert (vt[:, :, S:] == 0).all() and (k[:, S:] == 0).all()
+        assert torch.equal(k0, k.reshape(B * T, 6, Sp, 32)[:, 0]) and torch.equal(vt0, vt.reshape(B * T, 6, 32, Sp)[:, 0])
+
+
 def _one_layer_model(precision, seed=3):
     from multimodalpfn_b200.model import B200PerFeatureTransformer
     geom = Geometry(nlayers=1, mgm_heads=2, cap_heads=4)
