@@ -222,7 +222,8 @@ def run_ours(args):
     Ts = sorted({(g["F"] + 1) // 2 + 8 + 1 for g in eng.groups}, reverse=True)
 
     # ---- device-resident step -------------------------------------------------------------------
-    X_tests_host = [m.transform(X_test) for m in clf.members_]
+    from multimodalpfn_b200.preprocessing import transform_all
+    X_tests_host = transform_all(clf.members_, X_test)
     staged = eng.stage(X_tests_host, img_test)
     perms = [m.class_perm for m in clf.members_]
 

@@ -21,7 +21,7 @@ from sklearn.utils.validation import check_is_fitted
 
 from .engine import B200InferenceEngine, proba_from_logits
 from .model import B200PerFeatureTransformer
-from .preprocessing import RECIPES, make_members
+from .preprocessing import RECIPES, fit_transform_all, make_members, transform_all
 from .weights import load_checkpoint
 
 __all__ = ["MMPFNClassifier"]
@@ -131,10 +131,8 @@ class MMPFNClassifier(ClassifierMixin, BaseEstimator):
                                      recipes=tuple(recipes), fingerprint=icfg.get("FINGERPRINT_FEATURE", True),
                                      feature_shift=icfg.get("FEATURE_SHIFT_METHOD", "shuffle") is not None,
                                      class_shift=icfg.get("CLASS_SHIFT_METHOD", "shuffle") is not None)
-        members = []
-        for m in self.members_:
-            Xt, yt = m.fit_transform(X, yi)
-            members.append(dict(X_train=Xt, y_train=yt, class_perm=m.class_perm))
+        members = [dict(X_train=Xt, y_train=yt, class_perm=m.class_perm)
+                   for m, (Xt, yt) in zip(self.members_, fit_transform_all(self.members_, X, yi))]
         self.executor_ = B200InferenceEngine(self.model_, members, image,
                                              cache_context=(self.fit_mode == "fit_with_cache"))
         return self
@@ -167,7 +165,7 @@ class MMPFNClassifier(ClassifierMixin, BaseEstimator):
         """classifier.py:517-576."""
         check_is_fitted(self, "executor_")
         Xn = None if X is None else self._to_numeric(X, fit=False)
-        X_tests = [m.transform(Xn) for m in self.members_]
+        X_tests = transform_all(self.members_, Xn)
         if image_test is not None:
             image_test = np.asarray(image_test, dtype=np.float32)
             if image_test.ndim == 2:

@@ -23,7 +23,7 @@ from typing import Optional
 
 import numpy as np
 
-__all__ = ["EnsembleMember", "make_members", "RECIPES"]
+__all__ = ["EnsembleMember", "RecipeCore", "make_members", "fit_transform_all", "transform_all", "RECIPES"]
 
 RECIPES = ("quantile_svd", "none")
 
@@ -37,30 +37,22 @@ def _fingerprint(X: np.ndarray) -> np.ndarray:
     return out
 
 
-@dataclasses.dataclass
-class EnsembleMember:
-    recipe: str
-    feature_shift_seed: Optional[int]      # None = keep the column order
-    class_perm: Optional[np.ndarray]       # logits are gathered with it (classifier.py:550-551)
-    fingerprint: bool
-    feature_perm: Optional[np.ndarray] = None
-    numeric_cols: Optional[np.ndarray] = None
-    _qt: object = None
-    _svd: object = None
-    _svd_mean: Optional[np.ndarray] = None
-    _svd_scale: Optional[np.ndarray] = None
+class RecipeCore:
+    """The fitted, member-independent part of a recipe (quantile transformer, SVD basis).  Members of
+    the same recipe differ only in their feature / class permutations, so they share one core: it is
+    fitted once and, at predict time, applied once per call instead of once per member."""
 
-    def fit_transform(self, X: Optional[np.ndarray], y: np.ndarray):
-        """-> (X_train' or None, y_train permuted)."""
-        y_out = y if self.class_perm is None else self.class_perm[y]      # preprocessing.py:540-541
-        if X is None:
-            return None, y_out.astype(np.float32)
-        return self._apply(X, fit=True), y_out.astype(np.float32)
+    def __init__(self, recipe: str):
+        self.recipe = recipe
+        self.numeric_cols = None
+        self._qt = None
+        self._svd = None
+        self._svd_mean = None
+        self._svd_scale = None
+        self.fitted = False
 
-    def transform(self, X: Optional[np.ndarray]):
-        return None if X is None else self._apply(X, fit=False)
-
-    def _apply(self, X: np.ndarray, fit: bool) -> np.ndarray:
+    def features(self, X: np.ndarray, fit: bool) -> np.ndarray:
+        """Recipe columns for the raw table X (before fingerprint column and feature permutation)."""
         X = np.asarray(X, dtype=np.float32)
         parts = [X]
         if self.recipe == "quantile_svd":
@@ -85,9 +77,41 @@ class EnsembleMember:
                 self._svd = TruncatedSVD(n_components=k, algorithm="arpack", random_state=0)
                 self._svd.fit((Xz - self._svd_mean) / self._svd_scale)
             parts.append(self._svd.transform((Xz - self._svd_mean) / self._svd_scale).astype(np.float32))
-        out = np.concatenate(parts, 1)
+        if fit:
+            self.fitted = True
+        return np.concatenate(parts, 1)
+
+
+@dataclasses.dataclass
+class EnsembleMember:
+    recipe: str
+    feature_shift_seed: Optional[int]      # None = keep the column order
+    class_perm: Optional[np.ndarray]       # logits are gathered with it (classifier.py:550-551)
+    fingerprint: bool
+    feature_perm: Optional[np.ndarray] = None
+    core: Optional[RecipeCore] = None      # shared by the members of a recipe (make_members)
+
+    def __post_init__(self):
+        if self.core is None:
+            self.core = RecipeCore(self.recipe)
+
+    def fit_transform(self, X: Optional[np.ndarray], y: np.ndarray, *, base=None, fp=None):
+        """-> (X_train' or None, y_train permuted)."""
+        y_out = y if self.class_perm is None else self.class_perm[y]      # preprocessing.py:540-541
+        if X is None:
+            return None, y_out.astype(np.float32)
+        return self._apply(X, fit=True, base=base, fp=fp), y_out.astype(np.float32)
+
+    def transform(self, X: Optional[np.ndarray], *, base=None, fp=None):
+        return None if X is None else self._apply(X, fit=False, base=base, fp=fp)
+
+    def _apply(self, X: np.ndarray, fit: bool, base=None, fp=None) -> np.ndarray:
+        """``base`` / ``fp``: the recipe columns and the fingerprint column of X when the caller has
+        them already (fit_transform_all / transform_all compute each once per call)."""
+        X = np.asarray(X, dtype=np.float32)
+        out = self.core.features(X, fit and not self.core.fitted) if base is None else base
         if self.fingerprint:
-            out = np.concatenate([out, _fingerprint(X)[:, None]], 1)
+            out = np.concatenate([out, (_fingerprint(X) if fp is None else fp)[:, None]], 1)
         if self.feature_shift_seed is not None:
             if fit:
                 self.feature_perm = np.random.default_rng(self.feature_shift_seed).permutation(out.shape[1])
@@ -95,15 +119,44 @@ class EnsembleMember:
         return np.ascontiguousarray(out, dtype=np.float32)
 
 
+def _shared_parts(members, X: np.ndarray, fit: bool):
+    X = np.asarray(X, dtype=np.float32)
+    bases = {}
+    for m in members:
+        if id(m.core) not in bases:
+            bases[id(m.core)] = m.core.features(X, fit)
+    fp = _fingerprint(X) if any(m.fingerprint for m in members) else None
+    return X, bases, fp
+
+
+def fit_transform_all(members, X: Optional[np.ndarray], y: np.ndarray):
+    """All members at once: [(X_train', y_train')]; recipe cores are fitted once, the row fingerprint
+    is computed once."""
+    if X is None:
+        return [m.fit_transform(None, y) for m in members]
+    X, bases, fp = _shared_parts(members, X, fit=True)
+    return [m.fit_transform(X, y, base=bases[id(m.core)], fp=fp) for m in members]
+
+
+def transform_all(members, X: Optional[np.ndarray]):
+    """The test table of every member; the member-independent work (quantile / SVD projection,
+    per-row fingerprint hashing) is done once per call, not once per member."""
+    if X is None:
+        return [None for _ in members]
+    X, bases, fp = _shared_parts(members, X, fit=False)
+    return [m.transform(X, base=bases[id(m.core)], fp=fp) for m in members]
+
+
 def make_members(n_estimators: int, n_features: int, n_classes: int, rng: np.random.Generator, *,
                  recipes=RECIPES, fingerprint: bool = True, feature_shift: bool = True, class_shift: bool = True):
     """Balanced mix of the recipes, each with its own feature / class permutation
     (the structure of ``EnsembleConfig.generate_for_classification``, ``preprocessing.py:228-335``)."""
     members = []
+    cores = {}
     for e in range(n_estimators):
         recipe = recipes[e * len(recipes) // max(n_estimators, 1)] if n_estimators >= len(recipes) else recipes[e % len(recipes)]
         fseed = int(rng.integers(0, 2**31 - 1)) if feature_shift and n_features > 0 else None
         cperm = rng.permutation(n_classes) if class_shift else None
         members.append(EnsembleMember(recipe=recipe, feature_shift_seed=fseed, class_perm=cperm,
-                                      fingerprint=fingerprint))
+                                      fingerprint=fingerprint, core=cores.setdefault(recipe, RecipeCore(recipe))))
     return members
