@@ -26,13 +26,13 @@ constexpr int A_Q_BYTES = A_BQ * kD * 2;          // 8 KB  (64B rows, 64B swizzl
 constexpr int A_THREADS = 192;
 constexpr int kAttnPolyDefault = 4;
 
-template <int BK>
+template <int BK, bool PT = false>
 struct AttnCfg {
   static constexpr int kNKB = (BK + 63) / 64;                 // 64-key k-blocks of the P and V^T tiles
   static constexpr int kKTx = BK * kD * 2;                    // bytes of one K tile (64 B per key)
   static constexpr int kKSlot = BK > 64 ? 8192 : kKTx;          // slot stride: a multiple of 512 (the 64B-swizzle atom)
   static constexpr int kVtBytes = kNKB * kD * 128;            // [32 d][64 keys = 128 B] per k-block, 128B swizzle
-  static constexpr int kPBytes = kNKB * A_BQ * 128;           // [128 rows][128 B] per k-block, 128B swizzle
+  static constexpr int kPBytes = PT ? 0 : kNKB * A_BQ * 128;  // [128 rows][128 B] per k-block, 128B swizzle (P in TMEM: none)
   static constexpr int kOffK = A_Q_BYTES;
   static constexpr int kOffVt = kOffK + 2 * kKSlot;
   static constexpr int kOffP = (kOffVt + 2 * kVtBytes + 1023) / 1024 * 1024;
@@ -89,17 +89,45 @@ __device__ __forceinline__ void tmem_ld_cols(uint32_t taddr, uint32_t* v) {
   }
 }
 
+// n consecutive 32-bit columns of this warp's 32 TMEM lanes from v[0..n), n a multiple of 8
+template <int N>
+__device__ __forceinline__ void tmem_st_cols(uint32_t taddr, const uint32_t* v) {
+  static_assert(N % 8 == 0, "columns go in chunks of 8");
+  int c = 0;
+#pragma unroll
+  for (; c + 16 <= N; c += 16) {
+    asm volatile(
+        "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], "
+        "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16};"
+        ::"r"(taddr + c), "r"(v[c + 0]), "r"(v[c + 1]), "r"(v[c + 2]), "r"(v[c + 3]), "r"(v[c + 4]), "r"(v[c + 5]),
+          "r"(v[c + 6]), "r"(v[c + 7]), "r"(v[c + 8]), "r"(v[c + 9]), "r"(v[c + 10]), "r"(v[c + 11]), "r"(v[c + 12]),
+          "r"(v[c + 13]), "r"(v[c + 14]), "r"(v[c + 15])
+        : "memory");
+  }
+  if (N % 16 == 8) {
+    constexpr int c8 = N - 8;
+    asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};"
+                 ::"r"(taddr + c8), "r"(v[c8 + 0]), "r"(v[c8 + 1]), "r"(v[c8 + 2]), "r"(v[c8 + 3]), "r"(v[c8 + 4]),
+                   "r"(v[c8 + 5]), "r"(v[c8 + 6]), "r"(v[c8 + 7])
+                 : "memory");
+  }
+}
+
 //   warps 0-3  softmax, thread = query row (TMEM lane quarter = warp)
 //   warp 4     TMA producer (K and V^T on separate rings) + TMEM allocation
 //   warp 5     MMA issue: S = Q K^T into TMEM, O += P V with P read from shared memory
 // With S double buffered, S(j+2) is issued as soon as the softmax has pulled S(j) into registers, a
 // whole tile before it is needed: the mbarrier round trips (try_wait wake-up, tcgen05.commit arrival:
 // ~1900 cycles per tile measured with the math knocked out) leave the softmax path.
-template <int BK, int PN, int DBG>
-__global__ void __launch_bounds__(A_THREADS, AttnCfg<BK>::kMinCtas)
+// PT = true: P never touches shared memory.  The softmax writes it (bf16 pairs, 24 columns for 48 keys)
+// over the S columns it came from and the P V MMA reads its A operand from tensor memory: no st.shared,
+// no generic->async proxy fence (a full MEMBAR per thread and tile), and the S buffer of tile j simply
+// stays occupied until P V(j) has run — S(j+2) is issued right behind it by the same thread.
+template <int BK, int PN, int DBG, bool PT>
+__global__ void __launch_bounds__(A_THREADS, AttnCfg<BK, PT>::kMinCtas)
     tc_item_attn_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUtensorMap map_k,
                         const __grid_constant__ CUtensorMap map_vt, const AttnArgs p) {
-  using C = AttnCfg<BK>;
+  using C = AttnCfg<BK, PT>;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
   uint64_t* bars = (uint64_t*)(smem + C::kOffBar);
@@ -207,7 +235,7 @@ __global__ void __launch_bounds__(A_THREADS, AttnCfg<BK>::kMinCtas)
       for (int j = 0; j < nkt; ++j) {
         const int s = j & 1;
         const uint32_t ph = (j >> 1) & 1;
-        if (j + 2 < nkt) {
+        if (!PT && j + 2 < nkt) {
           // the TMA wait first: it is long satisfied and must not sit behind the softmax hand-off
           // K(j+2): completion (j+2)/2 of slot s; S(j) is in the softmax registers: its columns are free
           mbar_wait2(&k_full[s], ph ^ 1, &s_free[s], ph);
@@ -216,16 +244,30 @@ __global__ void __launch_bounds__(A_THREADS, AttnCfg<BK>::kMinCtas)
           issue_s(j + 2);
           ATTN_TRACE(2048 + j * 4 + 1);
         }
-        mbar_wait2(&v_full[s], ph, &p_full[s], ph);      // V^T(j) landed; P(j) is in shared memory
+        mbar_wait2(&v_full[s], ph, &p_full[s], ph);      // V^T(j) landed; P(j) is written (shared memory / TMEM)
         tc_fence_after();
         ATTN_TRACE(2048 + j * 4 + 2);
         if (!(DBG & 8)) {
-          const uint64_t pdesc = make_desc(sbase + C::kOffP + s * C::kPBytes, 1024, kSw128);
           const uint64_t vdesc = make_desc(sbase + C::kOffVt + s * C::kVtBytes, 1024, kSw128);
+          if (PT) {
 #pragma unroll
-          for (int k = 0; k < BK / 16; ++k)
-            umma_bf16(tmem_o, pdesc + (uint64_t)((k / 4) * ((A_BQ * 128) >> 4) + (k % 4) * 2),
-                      vdesc + (uint64_t)((k / 4) * ((kD * 128) >> 4) + (k % 4) * 2), idesc_o, (j | k) != 0);
+            for (int k = 0; k < BK / 16; ++k)
+              umma_bf16_ts(tmem_o, tmem + s * BK + k * 8,
+                           vdesc + (uint64_t)((k / 4) * ((kD * 128) >> 4) + (k % 4) * 2), idesc_o, (j | k) != 0);
+          } else {
+            const uint64_t pdesc = make_desc(sbase + C::kOffP + s * C::kPBytes, 1024, kSw128);
+#pragma unroll
+            for (int k = 0; k < BK / 16; ++k)
+              umma_bf16(tmem_o, pdesc + (uint64_t)((k / 4) * ((A_BQ * 128) >> 4) + (k % 4) * 2),
+                        vdesc + (uint64_t)((k / 4) * ((kD * 128) >> 4) + (k % 4) * 2), idesc_o, (j | k) != 0);
+          }
+        }
+        if (PT && j + 2 < nkt) {
+          // S(j+2) overwrites the columns P(j) sits in: issued behind P V(j) (tcgen05 ops of one thread
+          // execute in order)
+          mbar_wait(&k_full[s], ph ^ 1);
+          tc_fence_after();
+          issue_s(j + 2);
         }
         // ONE arrival tells the softmax both that S(j+2) is in TMEM buffer s and that P V(j) has
         // released P buffer s (tcgen05 ops complete in issue order), so its loop waits once per tile
@@ -298,6 +340,11 @@ __global__ void __launch_bounds__(A_THREADS, AttnCfg<BK>::kMinCtas)
         auto retire = [&](int k) {
           const float a = __uint_as_float(sv[2 * k]), b = __uint_as_float(sv[2 * k + 1]);
           lsum2 = add_f32x2(lsum2, pack_f32x2(a, b));
+          if (PT) {
+            // packed in place: slot k belonged to pair k / 2, retired no later than this one
+            sv[k] = pack_bf16x2(a, b);
+            return;
+          }
           pk[k & 3] = pack_bf16x2(a, b);
           if ((k & 3) == 3) {
             const int c16 = k >> 2;                           // 16-byte chunk of the row: keys 8*c16 .. +7
@@ -354,8 +401,12 @@ __global__ void __launch_bounds__(A_THREADS, AttnCfg<BK>::kMinCtas)
         }
         lsum = sweep(m_ref * c);
       }
-      tc_fence_before();
-      mbar_arrive_warp(&s_free[sb]);
+      if (PT) {
+        tmem_st_cols<BK / 2>(tmem_s, sv);          // P(j) over the first half of the S(j) columns
+      } else {
+        tc_fence_before();
+        mbar_arrive_warp(&s_free[sb]);
+      }
       l_run = l_run * alpha + lsum;
       if (threadIdx.x == 0) ATTN_TRACE(j * 8 + 4);
       // rescale the running output when some row of this warp moved its reference: needs P V(j-1)
@@ -371,7 +422,8 @@ __global__ void __launch_bounds__(A_THREADS, AttnCfg<BK>::kMinCtas)
         tmem_st_wait();
       }
       if (threadIdx.x == 0) ATTN_TRACE(j * 8 + 6);
-      fence_proxy_async();
+      if (PT) tmem_st_wait();
+      else fence_proxy_async();
       tc_fence_before();
       mbar_arrive_warp(&p_full[sb]);
       if (threadIdx.x == 0) ATTN_TRACE(j * 8 + 7);
@@ -403,19 +455,19 @@ __global__ void __launch_bounds__(A_THREADS, AttnCfg<BK>::kMinCtas)
   }
 }
 
-template <int BK, int PN, int DBG>
+template <int BK, int PN, int DBG, bool PT>
 void launch_attn_t(const CUtensorMap& mq, const CUtensorMap& mk, const CUtensorMap& mvt, const AttnArgs& a, dim3 grid,
                    cudaStream_t st) {
-  using C = AttnCfg<BK>;
+  using C = AttnCfg<BK, PT>;
   static bool configured = false;
   if (!configured) {
-    cudaFuncSetAttribute(tc_item_attn_kernel<BK, PN, DBG>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::kSmem);
+    cudaFuncSetAttribute(tc_item_attn_kernel<BK, PN, DBG, PT>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::kSmem);
     configured = true;
   }
-  tc_item_attn_kernel<BK, PN, DBG><<<grid, A_THREADS, C::kSmem, st>>>(mq, mk, mvt, a);
+  tc_item_attn_kernel<BK, PN, DBG, PT><<<grid, A_THREADS, C::kSmem, st>>>(mq, mk, mvt, a);
 }
 
-template <int BK>
+template <int BK, bool PT>
 int launch_attn_bk(const TcItemAttn& p, int poly, int dbg, cudaStream_t st) {
   const long long planes_q = (long long)p.B * p.T * kH;
   const long long planes_kv = p.shared_kv ? (long long)p.B * p.T : planes_q;
@@ -444,19 +496,19 @@ int launch_attn_bk(const TcItemAttn& p, int poly, int dbg, cudaStream_t st) {
   const dim3 grid((unsigned)(planes_q * q_tiles));
   if (dbg) {
     switch (dbg) {
-      case 1: launch_attn_t<BK, 0, 1>(mq, mk, mvt, a, grid, st); break;
-      case 8: launch_attn_t<BK, 0, 8>(mq, mk, mvt, a, grid, st); break;
-      case 63: launch_attn_t<BK, 0, 63>(mq, mk, mvt, a, grid, st); break;
-      case 64: launch_attn_t<BK, 0, 64>(mq, mk, mvt, a, grid, st); break;
+      case 1: launch_attn_t<BK, 0, 1, PT>(mq, mk, mvt, a, grid, st); break;
+      case 8: launch_attn_t<BK, 0, 8, PT>(mq, mk, mvt, a, grid, st); break;
+      case 63: launch_attn_t<BK, 0, 63, PT>(mq, mk, mvt, a, grid, st); break;
+      case 64: launch_attn_t<BK, 0, 64, PT>(mq, mk, mvt, a, grid, st); break;
       default: set_error("unknown MMPFN_ATTN_DBG"); return MMPFN_EINVAL;
     }
     return count_launch();
   }
   switch (poly) {
-    case 4: launch_attn_t<BK, 4, 0>(mq, mk, mvt, a, grid, st); break;
-    case 8: launch_attn_t<BK, 8, 0>(mq, mk, mvt, a, grid, st); break;
-    case 12: launch_attn_t<BK, 12, 0>(mq, mk, mvt, a, grid, st); break;
-    default: launch_attn_t<BK, 0, 0>(mq, mk, mvt, a, grid, st); break;
+    case 4: launch_attn_t<BK, 4, 0, PT>(mq, mk, mvt, a, grid, st); break;
+    case 8: launch_attn_t<BK, 8, 0, PT>(mq, mk, mvt, a, grid, st); break;
+    case 12: launch_attn_t<BK, 12, 0, PT>(mq, mk, mvt, a, grid, st); break;
+    default: launch_attn_t<BK, 0, 0, PT>(mq, mk, mvt, a, grid, st); break;
   }
   return count_launch();
 }
@@ -468,7 +520,7 @@ int launch_tc_item_attn(const TcItemAttn& p, cudaStream_t st) {
   if (p.n_kv <= 0) { set_error("item attention: empty key set"); return MMPFN_EINVAL; }
   // MMPFN_ATTN_POLY (0..16, read once): how many of every 32 exponentials leave the MUFU pipe for
   // the FMA-pipe polynomial; MMPFN_ATTN_BK: keys per tile (112 or 48).  Defaults = measured optimum.
-  static int poly = -1, dbg = 0, bk = 48;
+  static int poly = -1, dbg = 0, bk = 48, pt = 1;
   if (poly < 0) {
     const char* e = getenv("MMPFN_ATTN_POLY");
     poly = e ? atoi(e) : kAttnPolyDefault;
@@ -476,9 +528,12 @@ int launch_tc_item_attn(const TcItemAttn& p, cudaStream_t st) {
     dbg = e ? atoi(e) : 0;
     e = getenv("MMPFN_ATTN_BK");
     bk = e ? atoi(e) : 48;
+    e = getenv("MMPFN_ATTN_PT");          // 0: P through shared memory (the older hand-off), A/B timing only
+    pt = e ? atoi(e) : 1;
   }
-  if (bk == 112) return launch_attn_bk<112>(p, poly, dbg, st);
-  return launch_attn_bk<48>(p, poly, dbg, st);
+  if (bk == 112) return launch_attn_bk<112, false>(p, poly, dbg, st);
+  if (!pt) return launch_attn_bk<48, false>(p, poly, dbg, st);
+  return launch_attn_bk<48, true>(p, poly, dbg, st);
 }
 
 }  // namespace mmpfn
