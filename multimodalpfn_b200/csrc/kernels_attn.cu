@@ -293,6 +293,7 @@ __global__ void __launch_bounds__(A_THREADS, AttnCfg<BK, PT>::kMinCtas)
     constexpr int kAhead = 4;                    // pairs whose scaled argument is ready ahead of their ex2
     constexpr int kBehind = 5;                   // pairs whose ex2 is in flight before the first consumer reads one
     float m_ref = -INFINITY, l_run = 0.f;
+    bool next_ready = false;
     uint32_t sv[BK];
     for (int j = 0; j < nkt; ++j) {
       const int sb = j & 1;
@@ -300,7 +301,9 @@ __global__ void __launch_bounds__(A_THREADS, AttnCfg<BK, PT>::kMinCtas)
       const uint32_t pbuf = prow_s + sb * C::kPBytes;
       const int valid = p.n_kv - j * BK;         // keys of this tile that exist
       if (threadIdx.x == 0) ATTN_TRACE(j * 8 + 0);
-      mbar_wait(&s_full[sb], (j >> 1) & 1);      // S(j) is in TMEM and P buffer sb is free (P V(j-2) done)
+      // S(j) is in TMEM and P buffer sb is free (P V(j-2) done).  Usually the probe made at the end of
+      // the previous tile has already said so.
+      if (!next_ready) mbar_wait(&s_full[sb], (j >> 1) & 1);
       tc_fence_after();
       if (threadIdx.x == 0) ATTN_TRACE(j * 8 + 1);
       // the whole row of S into registers (masking the keys a partial last tile does not have)
@@ -389,6 +392,8 @@ __global__ void __launch_bounds__(A_THREADS, AttnCfg<BK, PT>::kMinCtas)
       // place, so the repeat reads it from TMEM again: the S columns are handed back to the MMA warp
       // only after the decision (S is double buffered: no one is waiting).
       float lsum = sweep(m_ref * c);
+      // early probe of the next tile's S: consumed at the top of the next iteration
+      const bool probe = j + 1 < nkt && mbar_test(&s_full[sb ^ 1], ((j + 1) >> 1) & 1);
       const bool moved = !(lsum <= kSumLimit) && !(DBG & 32);
       const bool any_moved = __any_sync(0xffffffffu, moved);   // tcgen05.ld is warp-collective
       float alpha = 1.0f;
@@ -426,6 +431,7 @@ __global__ void __launch_bounds__(A_THREADS, AttnCfg<BK, PT>::kMinCtas)
       else fence_proxy_async();
       tc_fence_before();
       mbar_arrive_warp(&p_full[sb]);
+      next_ready = __all_sync(0xffffffffu, probe);
       if (threadIdx.x == 0) ATTN_TRACE(j * 8 + 7);
     }
     uint32_t v[32];

@@ -76,6 +76,19 @@ __device__ __forceinline__ bool elect_one() {
   asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(pred));
   return pred != 0;
 }
+// Non-blocking probe: has the phase with this parity completed?  The answer can be consumed much later
+// (the probe's ~200-cycle round trip then hides under other work) and a positive one replaces the wait.
+__device__ __forceinline__ bool mbar_test(uint64_t* bar, uint32_t parity) {
+  uint32_t done;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(done)
+      : "r"(smem_u32(bar)), "r"(parity)
+      : "memory");
+  return done != 0;
+}
 // Wait for two barriers at once.  Even a wait that is already satisfied costs the calling thread
 // ~200-250 cycles (SYNCS round trip): a single-thread issue loop that checks two barriers per step
 // pays it once instead of twice when both probes are in flight together.
