@@ -126,7 +126,9 @@ int mmpfn_stem_image(const mmpfn_geometry* g, const mmpfn_weights* w, const floa
  *   x       [B][.][F] or NULL: S rows per estimator starting at x, estimators x_bstride elements apart
  *           (so the train rows and the test rows of one [B][S_full][F] table embed separately)
  *   stats   [B][tab_stats_elems] or NULL
- *   img_tok [S][H_img][E] or NULL      (shared by the B estimators, inference.py:272)
+ *   img_tok [S][H_img][E] or NULL: batch entry b reads img_tok + b * img_bstride (elements); img_bstride = 0
+ *           = one set shared by the B estimators of a task (inference.py:272), S*H_img*E = one per entry
+ *           (independent tasks packed on the batch axis)
  *   y       [B][.]: S labels per estimator, y_bstride apart (NaN = unlabeled test row)
  *   y_mean  [B], y_present_mask [B] (bit c set iff class c occurs among the train labels)
  *   pos_emb [T-1][E]
@@ -134,7 +136,7 @@ int mmpfn_stem_image(const mmpfn_geometry* g, const mmpfn_weights* w, const floa
  * nan_flag (int32, device): set to 1 if any produced value is NaN (transformer.py:727-731, :790-796). */
 int mmpfn_stem_tokens(const mmpfn_geometry* g, const mmpfn_weights* w, const float* x, const float* stats,
                       const float* img_tok, const float* y, const float* y_mean, const uint64_t* y_present_mask,
-                      const float* pos_emb, int B, int S, int F, int H_img, long long x_bstride, long long y_bstride,
+                      const float* pos_emb, int B, int S, int F, int H_img, long long x_bstride, long long y_bstride, long long img_bstride,
                       float* state_f32, uint16_t* state_bf16, int32_t* nan_flag, void* stream);
 
 /* ---- the 12 layers ------------------------------------------------------------------------- */

@@ -47,7 +47,7 @@ SIGNATURES = {
     "mmpfn_stem_image_ws_bytes": (c_size_t, [PG, c_int, c_int]),
     "mmpfn_stem_image": (c_int, [PG, PW, c_void_p, c_int, c_int, c_void_p, c_void_p, c_size_t, c_void_p]),
     "mmpfn_stem_tokens": (c_int, [PG, PW, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p,
-                                  c_int, c_int, c_int, c_int, c_ll, c_ll, c_void_p, c_void_p, c_void_p, c_void_p]),
+                                  c_int, c_int, c_int, c_int, c_ll, c_ll, c_ll, c_void_p, c_void_p, c_void_p, c_void_p]),
     "mmpfn_layers_ws_bytes": (c_size_t, [PG, c_int, c_int, c_int, c_int]),
     "mmpfn_kv_bytes": (c_size_t, [PG, c_int, c_int, c_int, c_int]),
     "mmpfn_layers_train": (c_int, [PG, PW, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p,

@@ -286,16 +286,17 @@ int mmpfn_stem_image(const mmpfn_geometry* g, const mmpfn_weights* w, const floa
 int mmpfn_stem_tokens(const mmpfn_geometry* g, const mmpfn_weights* w, const float* x, const float* stats,
                       const float* img_tok, const float* y, const float* y_mean, const uint64_t* y_present_mask,
                       const float* pos_emb, int B, int S, int F, int H_img, long long x_bstride, long long y_bstride,
-                      float* state_f32, uint16_t* state_bf16, int32_t* nan_flag, void* stream) {
+                      long long img_bstride, float* state_f32, uint16_t* state_bf16, int32_t* nan_flag, void* stream) {
   MMPFN_TRY(check_geometry(g));
   MMPFN_TRY(require_device());
   if (!w || !y || !y_mean || !y_present_mask || !pos_emb || !state_f32 || !nan_flag || B < 1 || S < 1 ||
-      (x && (!stats || F < 1)) || (!x && !img_tok) || (img_tok && H_img < 1) || (!img_tok && H_img != 0)) {
+      (x && (!stats || F < 1)) || (!x && !img_tok) || (img_tok && H_img < 1) || (!img_tok && H_img != 0) ||
+      img_bstride < 0) {
     set_error("stem_tokens: bad arguments");
     return MMPFN_EINVAL;
   }
   return launch_stem_tokens(g, w, x, stats, img_tok, y, y_mean, y_present_mask, pos_emb, B, S, x ? F : 0, H_img,
-                            x_bstride, y_bstride, state_f32, state_bf16, nan_flag, (cudaStream_t)stream);
+                            x_bstride, y_bstride, img_bstride, state_f32, state_bf16, nan_flag, (cudaStream_t)stream);
 }
 
 size_t mmpfn_layers_ws_bytes(const mmpfn_geometry* g, int B, int S, int T, int precision) {

@@ -166,7 +166,7 @@ int launch_tab_fit(const float* x, int B, int S, int F, int fpg, int n_train, fl
 int launch_stem_tokens(const mmpfn_geometry* g, const mmpfn_weights* w, const float* x, const float* stats,
                        const float* img_tok, const float* y, const float* y_mean, const uint64_t* y_mask,
                        const float* pos_emb, int B, int S, int F, int H_img, long long x_bstride, long long y_bstride,
-                       float* state_f32, uint16_t* state_bf16, int32_t* nan_flag, cudaStream_t st);
+                       long long img_bstride, float* state_f32, uint16_t* state_bf16, int32_t* nan_flag, cudaStream_t st);
 int launch_cap_attn(const float* kv, const float* q, int S, int n_kv, int Hc, float* out, cudaStream_t st);
 int launch_cap_combine(const float* o, const float* ffn, const float* gamma, const float* beta, long long rows,
                        float* out, cudaStream_t st);

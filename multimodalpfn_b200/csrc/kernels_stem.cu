@@ -171,7 +171,7 @@ __global__ void __launch_bounds__(kE) stem_tokens_kernel(
     const float* __restrict__ y, const float* __restrict__ y_mean, const uint64_t* __restrict__ y_mask,
     const float* __restrict__ pos_emb, const float* __restrict__ enc_w, const float* __restrict__ yenc_w,
     const float* __restrict__ yenc_b, int S, int F, int fpg, int G, int H_img, long long x_bstride,
-    long long y_bstride, float* __restrict__ state, uint16_t* __restrict__ state_bf,
+    long long y_bstride, long long img_bstride, float* __restrict__ state, uint16_t* __restrict__ state_bf,
     int32_t* __restrict__ nan_flag) {
   const int e = threadIdx.x;
   const long long s = blockIdx.x;
@@ -214,8 +214,9 @@ __global__ void __launch_bounds__(kE) stem_tokens_kernel(
     }
   }
   // image / text tokens appended after the tabular ones (transformer.py:768, :1038)
+  // (img_bstride = 0: one set of tokens shared by the B estimators of a task; otherwise one per batch entry)
   for (int h = 0; h < H_img; ++h)
-    emit(G + h, img_tok[((long long)s * H_img + h) * kE + e] + pos_emb[(G + h) * kE + e]);
+    emit(G + h, img_tok[b * img_bstride + ((long long)s * H_img + h) * kE + e] + pos_emb[(G + h) * kE + e]);
   // y token, last (encoders.py:480-493 indicator/fill, :961-964 ordinal rank, :422-425 Linear(2 -> E) + b)
   {
     float yy = y[b * y_bstride + s];
@@ -375,12 +376,12 @@ int launch_tab_fit(const float* x, int B, int S, int F, int fpg, int n_train, fl
 int launch_stem_tokens(const mmpfn_geometry* g, const mmpfn_weights* w, const float* x, const float* stats,
                        const float* img_tok, const float* y, const float* y_mean, const uint64_t* y_mask,
                        const float* pos_emb, int B, int S, int F, int H_img, long long x_bstride, long long y_bstride,
-                       float* state_f32, uint16_t* state_bf16, int32_t* nan_flag, cudaStream_t st) {
+                       long long img_bstride, float* state_f32, uint16_t* state_bf16, int32_t* nan_flag, cudaStream_t st) {
   const int fpg = g->features_per_group;
   const int G = x ? (F + fpg - 1) / fpg : 0;
   if (fpg > 4) { set_error("features_per_group %d > 4", fpg); return MMPFN_EUNSUPPORTED; }
   stem_tokens_kernel<<<dim3(S, B), kE, 0, st>>>(x, stats, img_tok, y, y_mean, y_mask, pos_emb, w->enc_w, w->yenc_w,
-                                               w->yenc_b, S, F, fpg, G, H_img, x_bstride, y_bstride, state_f32, state_bf16,
+                                               w->yenc_b, S, F, fpg, G, H_img, x_bstride, y_bstride, img_bstride, state_f32, state_bf16,
                                                nan_flag);
   return count_launch();
 }

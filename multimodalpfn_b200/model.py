@@ -177,7 +177,14 @@ class B200PerFeatureTransformer:
     def embed(self, X, stats, img_tok, y, y_mean, y_mask, pos_emb, *, B, S, F, x_bstride, y_bstride, nan_flag):
         """Token assembly -> (state_f32 [B,S,T,E], state_bf16 or None)."""
         G = self._n_groups(F) if X is not None else 0
-        H_img = 0 if img_tok is None else img_tok.shape[1]
+        # img_tok [S, H, E]: shared by the B entries; [B, S, H, E]: one set per entry (packed tasks)
+        H_img = 0 if img_tok is None else img_tok.shape[-2]
+        img_bstride = 0
+        if img_tok is not None and img_tok.dim() == 4:
+            if img_tok.shape[0] != B or img_tok.shape[1] != S:
+                raise ValueError("per-entry image tokens must be [B, S, H, E]")
+            img_tok = img_tok.contiguous()
+            img_bstride = img_tok.shape[1] * img_tok.shape[2] * img_tok.shape[3]
         T = G + H_img + 1
         E = self.geom.emsize
         state = torch.empty((B, S, T, E), dtype=torch.float32, device=self.device)
@@ -186,7 +193,7 @@ class B200PerFeatureTransformer:
         _lib.check(self.lib.mmpfn_stem_tokens(
             self._g, self._w, _ptr(X), _ptr(stats), _ptr(img_tok), y.data_ptr(), y_mean.data_ptr(),
             y_mask.data_ptr(), pos_emb.data_ptr(), B, S, F if X is not None else 0, H_img, x_bstride, y_bstride,
-            state.data_ptr(), _ptr(state_b), nan_flag.data_ptr(), self._stream()), "mmpfn_stem_tokens")
+            img_bstride, state.data_ptr(), _ptr(state_b), nan_flag.data_ptr(), self._stream()), "mmpfn_stem_tokens")
         return state, state_b
 
     # ------------------------------------------------------------------ layers / decoder
@@ -271,7 +278,7 @@ class B200PerFeatureTransformer:
             # label statistics involve a host sync: callers that replay a CUDA graph pass them in
             y_mean, y_mask = label_stats if label_stats is not None else self.label_stats(y_train)
             G = self._n_groups(F) if X_train is not None else 0
-            H_img = 0 if img_tok_train is None else img_tok_train.shape[1]
+            H_img = 0 if img_tok_train is None else img_tok_train.shape[-2]
             T = G + H_img + 1
             pos = self.positional_embeddings(T - 1)
             flag = nan_flag if nan_flag is not None else torch.zeros(1, dtype=torch.int32, device=self.device)
@@ -291,7 +298,7 @@ class B200PerFeatureTransformer:
             X_test, img_test = self._prep(X_test, img_test)
             if img_tok_test is None and img_test is not None:
                 img_tok_test = self.stem_image(img_test)
-            n_test = X_test.shape[1] if X_test is not None else img_tok_test.shape[0]
+            n_test = X_test.shape[1] if X_test is not None else img_tok_test.shape[-3]
             if X_test is not None and (X_test.shape[0] != ctx.B or X_test.shape[2] != ctx.F):
                 raise ValueError(f"test table {tuple(X_test.shape)} does not match the context (B {ctx.B}, F {ctx.F})")
             y_nan = torch.full((1, n_test), float("nan"), dtype=torch.float32, device=self.device)
