@@ -132,14 +132,34 @@ class ShardedEngine:
             ctxs[si] = TrainContext(B=B, n_train=n_tr, F=F, T=T, n_tok=0, kv=got[0], tab_stats=got[3] if G else None,
                                     y_mean=got[1], y_mask=got[2], pos_emb=m.positional_embeddings(T - 1),
                                     precision=m.precision)
-        # 3. this rank's test rows against every context
+        # 3. this rank's test rows against every context.  The contexts of a group's estimators arrive
+        #    from different owners; they are merged back into ONE batched context per group so that the
+        #    test pass launches once per group (B = 4 here) instead of once per owner (B = 1 at W = 8:
+        #    8 x as many launches of kernels that are already latency bound at 300 rows).
         tok_test = None if tok is None else tok[n_img_train:]
-        for si, sub in enumerate(self.subs):
-            Xte = staged["X_test"][sub.group]
-            Xte = None if Xte is None else Xte[sub.pos].contiguous()
-            lg = m.predict_with_context(ctxs[si], Xte, None, img_tok_test=tok_test, check=False,
+        for gi, g in enumerate(eng.groups):
+            subs = [(si, sub) for si, sub in enumerate(self.subs) if sub.group == gi]
+            if len(subs) == 1:
+                ctx = ctxs[subs[0][0]]
+            else:
+                Bg = len(g["idx"])
+                c0 = ctxs[subs[0][0]]
+                y_mean = torch.empty(Bg, dtype=c0.y_mean.dtype, device=dev)
+                y_mask = torch.empty(Bg, dtype=c0.y_mask.dtype, device=dev)
+                stats = None if c0.tab_stats is None else torch.empty((Bg,) + tuple(c0.tab_stats.shape[1:]),
+                                                                      dtype=c0.tab_stats.dtype, device=dev)
+                for si, sub in subs:
+                    c = ctxs[si]
+                    y_mean[sub.pos] = c.y_mean
+                    y_mask[sub.pos] = c.y_mask
+                    if stats is not None:
+                        stats[sub.pos] = c.tab_stats
+                kv = m.merge_kv([(ctxs[si].kv, sub.pos) for si, sub in subs], Bg, c0.n_train, c0.T)
+                ctx = TrainContext(B=Bg, n_train=c0.n_train, F=c0.F, T=c0.T, n_tok=0, kv=kv, tab_stats=stats,
+                                   y_mean=y_mean, y_mask=y_mask, pos_emb=c0.pos_emb, precision=m.precision)
+            lg = m.predict_with_context(ctx, staged["X_test"][gi], None, img_tok_test=tok_test, check=False,
                                         nan_flag=eng.nan_flag)
-            for k, i in enumerate(sub.members):
+            for k, i in enumerate(g["idx"]):
                 out[i] = lg[k]
         return torch.stack(out)
 

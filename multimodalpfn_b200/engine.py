@@ -112,7 +112,8 @@ class B200InferenceEngine:
         DMA transfers from pinned memory, not staged pageable copies."""
         buf = self._pinned_bufs.get(key)
         if buf is None or tuple(buf.shape) != tuple(shape):
-            buf = torch.empty(tuple(shape), dtype=torch.float32, pin_memory=True)
+            # (the CPU stand-in model of the gloo tests has no driver to pin memory with)
+            buf = torch.empty(tuple(shape), dtype=torch.float32, pin_memory=self.model.device.type == "cuda")
             self._pinned_bufs[key] = buf
         return buf
 
@@ -141,8 +142,9 @@ class B200InferenceEngine:
                 Xte.append(pin.to(dev, non_blocking=True))
             else:
                 Xte.append(None)
-        self._stage_event = torch.cuda.Event()
-        self._stage_event.record(torch.cuda.current_stream(dev))
+        if dev.type == "cuda":
+            self._stage_event = torch.cuda.Event()
+            self._stage_event.record(torch.cuda.current_stream(dev))
         return dict(X_test=Xte, img_test=img_test_dev)
 
     def logits_staged(self, staged) -> torch.Tensor:

@@ -218,6 +218,25 @@ class B200PerFeatureTransformer:
         # zero-filled: the bf16 layout pads the row axis to a multiple of 64
         return torch.zeros(nbytes, dtype=torch.uint8, device=self.device)
 
+    def merge_kv(self, parts, B: int, n_train: int, T: int) -> torch.Tensor:
+        """Assemble the K/V context of a batch of B estimators from contexts built for subsets of it
+        (``parts``: [(kv, positions within the batch)]) — the layer axis is outermost in the context
+        layout, so every subset lands as L strided slabs (one device copy per subset)."""
+        L = self.geom.nlayers
+        out = torch.empty(self.lib.mmpfn_kv_bytes(self._g, B, n_train, T, self.precision), dtype=torch.uint8,
+                          device=self.device)
+        if self.precision == _lib.BF16:       # per layer: K0 [B][T][Sp][32] then V0^T [B][T][32][Sp]
+            per_b = out.numel() // (L * 2 * B)
+            dst = out.view(L, 2, B, per_b)
+            for kv, pos in parts:
+                dst[:, :, pos] = kv.view(L, 2, len(pos), per_b)
+        else:                                  # per layer: [B][T][n][2][32] fp32
+            per_b = out.numel() // (L * B)
+            dst = out.view(L, B, per_b)
+            for kv, pos in parts:
+                dst[:, pos] = kv.view(L, len(pos), per_b)
+        return out
+
     def decode(self, state: torch.Tensor) -> torch.Tensor:
         """[B,S,T,E] -> logits [B,S,n_out] (transformer.py:850-853)."""
         B, S, T, _ = state.shape
