@@ -325,10 +325,16 @@ def run_ours(args):
             evc.append((a, b))
         torch.cuda.synchronize()
         msc = float(np.mean([a.elapsed_time(b) for a, b in evc]))
-        t0 = time.perf_counter()
+        for _ in range(2):
+            clf_c.predict_proba(X_test, img_test)
+        e2e_c = []
         for _ in range(args.steps):
+            flush.zero_()
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
             pc = clf_c.predict_proba(X_test, img_test)
-        e2ec = (time.perf_counter() - t0) / args.steps
+            e2e_c.append(time.perf_counter() - t0)
+        e2ec = float(np.mean(e2e_c))
         cached = {"value": n_te / (msc * 1e-3), "unit": "rows/s", "ms_per_step": msc,
                   "e2e": {"value": n_te / e2ec, "unit": "rows/s", "ms_per_step": e2ec * 1e3},
                   "max_abs_dp_vs_rebuilt": float(np.abs(pc - p).max()),
