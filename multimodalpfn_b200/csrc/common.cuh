@@ -3,7 +3,6 @@
 #include <cuda_bf16.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
-#include <stdlib.h>
 
 #include <atomic>
 
@@ -30,38 +29,6 @@ inline int count_launch() {
     return MMPFN_ECUDA;
   }
   return MMPFN_OK;
-}
-
-// Programmatic dependent launch.  A kernel launched through launch_pdl may begin (barrier setup, TMEM
-// allocation, tensor-map prefetch, weight loads) while the previous kernel of the stream is still draining;
-// it must call pdl_wait() before it touches anything a previous kernel reads or writes.  Every kernel calls
-// pdl_trigger() first thing, which lets its successor in as soon as all of its own CTAs have started.
-// MMPFN_PDL=0 turns the launch attribute off (plain stream order).
-__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
-__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
-
-inline bool pdl_enabled() {
-  static int on = -1;
-  if (on < 0) {
-    const char* e = getenv("MMPFN_PDL");
-    on = e ? atoi(e) : 1;
-  }
-  return on != 0;
-}
-
-template <typename... KArgs, typename... Args>
-inline void launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args&&... args) {
-  cudaLaunchConfig_t cfg = {};
-  cfg.gridDim = grid;
-  cfg.blockDim = block;
-  cfg.dynamicSmemBytes = smem;
-  cfg.stream = st;
-  cudaLaunchAttribute attr[1];
-  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-  attr[0].val.programmaticStreamSerializationAllowed = 1;
-  cfg.attrs = attr;
-  cfg.numAttrs = pdl_enabled() ? 1 : 0;
-  cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
 }
 
 #define MMPFN_TRY(expr)            \

@@ -153,7 +153,6 @@ __global__ void __launch_bounds__(A_THREADS, AttnCfg<BK, PT>::kMinCtas)
   const int kv_plane = p.shared_kv ? bt : plane;
   const int nkt = (p.n_kv + BK - 1) / BK;
 
-  pdl_trigger();
   if (threadIdx.x == 0) {
     prefetch_tmap(&map_q);
     prefetch_tmap(&map_k);
@@ -177,7 +176,6 @@ __global__ void __launch_bounds__(A_THREADS, AttnCfg<BK, PT>::kMinCtas)
   tc_fence_after();
   const uint32_t tmem = *tmem_slot;
   const uint32_t tmem_o = tmem + 2 * BK;
-  pdl_wait();          // everything above overlapped the previous kernel's tail; q/k/v^T are its output
 
   if (warp == 4) {
     if (elect_one()) {
@@ -472,7 +470,7 @@ void launch_attn_t(const CUtensorMap& mq, const CUtensorMap& mk, const CUtensorM
     cudaFuncSetAttribute(tc_item_attn_kernel<BK, PN, DBG, PT>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::kSmem);
     configured = true;
   }
-  launch_pdl(tc_item_attn_kernel<BK, PN, DBG, PT>, grid, dim3(A_THREADS), C::kSmem, st, mq, mk, mvt, a);
+  tc_item_attn_kernel<BK, PN, DBG, PT><<<grid, A_THREADS, C::kSmem, st>>>(mq, mk, mvt, a);
 }
 
 template <int BK, bool PT>

@@ -297,8 +297,6 @@ template <int KT>
 __global__ void __launch_bounds__(384) feat_attn_mma_kernel(const uint16_t* __restrict__ qkv,
                                                             uint16_t* __restrict__ att, int T) {
   extern __shared__ __align__(16) uint8_t fsm[];
-  pdl_trigger();
-  pdl_wait();
   const long long row = blockIdx.x;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int n_kt = (T + 15) >> 4;               // 16-key tiles actually present
@@ -423,7 +421,7 @@ int launch_feat_attn_mma_t(const uint16_t* qkv, uint16_t* att, long long n_seq, 
   }
   const int n_items = kH * (Tp / 16);
   const int warps = n_items < 12 ? n_items : 12;
-  launch_pdl(kern, dim3((unsigned)n_seq), dim3(warps * 32), smem, st, qkv, att, T);
+  kern<<<(unsigned)n_seq, warps * 32, smem, st>>>(qkv, att, T);
   return count_launch();
 }
 }  // namespace

@@ -135,7 +135,6 @@ __global__ void __launch_bounds__(F_THREADS, 1) tc_mlp_kernel(const __grid_const
   const int my_tiles = (p.n_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
   const int G = my_tiles * F_NCH;      // chunks this CTA walks, flat over its tiles
 
-  pdl_trigger();
   if (threadIdx.x == 0) {
     prefetch_tmap(&map_a);
     prefetch_tmap(&map_w1);
@@ -167,9 +166,6 @@ __global__ void __launch_bounds__(F_THREADS, 1) tc_mlp_kernel(const __grid_const
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem = *tmem_slot;
-  // the state (activations, residual) is the previous kernel's output; W1/W2 are not, but their first
-  // chunks follow the activation tile within a microsecond anyway
-  pdl_wait();
 
   if (warp == 0) {
     if (elect_one()) {
@@ -473,8 +469,8 @@ int launch_tc_mlp(const TcMlp& p, cudaStream_t st) {
   a.n_tiles = (p.M + F_BM - 1) / F_BM;
   a.state_b = p.state_b;
   const int grid = a.n_tiles < n_sm ? a.n_tiles : n_sm;
-  if (dbg) launch_pdl(tc_mlp_kernel<1>, dim3(grid), dim3(F_THREADS), F_SMEM, st, ma, mw1, mw2, mr, my, a);
-  else launch_pdl(tc_mlp_kernel<0>, dim3(grid), dim3(F_THREADS), F_SMEM, st, ma, mw1, mw2, mr, my, a);
+  if (dbg) tc_mlp_kernel<1><<<grid, F_THREADS, F_SMEM, st>>>(ma, mw1, mw2, mr, my, a);
+  else tc_mlp_kernel<0><<<grid, F_THREADS, F_SMEM, st>>>(ma, mw1, mw2, mr, my, a);
   return count_launch();
 }
 

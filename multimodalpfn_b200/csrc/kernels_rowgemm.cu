@@ -97,7 +97,6 @@ __global__ void __launch_bounds__(R_THREADS, 1) tc_rowgemm_kernel(const __grid_c
   const int cid = (int)blockIdx.x / p.n_tiles;         // its position among the CTAs of that n-tile
   const int my_tiles = cid < p.m_tiles ? (p.m_tiles - cid + p.ctas_per_n - 1) / p.ctas_per_n : 0;
 
-  pdl_trigger();
   if (threadIdx.x == 0) {
     prefetch_tmap(&map_a);
     prefetch_tmap(&map_w);
@@ -134,11 +133,9 @@ __global__ void __launch_bounds__(R_THREADS, 1) tc_rowgemm_kernel(const __grid_c
 
   if (warp == 0) {
     if (elect_one()) {
-      // the weights are not written by any kernel of the step: their load overlaps the previous kernel
       mbar_expect_tx(w_full, R_W_BYTES);
 #pragma unroll
       for (int kb = 0; kb < 3; ++kb) tma_load_2d(smem + R_OFF_W + kb * (R_BN * 128), &map_w, w_full, kb * 64, jn * R_BN);
-      pdl_wait();
       auto load_a = [&](int i) {
         const int mt = tile_of(i);
         const int as = i % kAStages;
@@ -197,7 +194,6 @@ __global__ void __launch_bounds__(R_THREADS, 1) tc_rowgemm_kernel(const __grid_c
       }
     }
   } else if (warp >= 4) {
-    pdl_wait();          // the epilogue writes buffers the previous kernel may still be reading
     const int quarter = warp & 3;
     const int r = quarter * 32 + lane;
     const int rsw = r & 7;
@@ -381,7 +377,7 @@ int launch_rowgemm_t(const CUtensorMap& ma, const CUtensorMap& mw, const CUtenso
     cudaFuncSetAttribute(tc_rowgemm_kernel<EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, R_SMEM);
     configured = true;
   }
-  launch_pdl(tc_rowgemm_kernel<EPI>, dim3(grid), dim3(R_THREADS), R_SMEM, st, ma, mw, mr, my, im, a);
+  tc_rowgemm_kernel<EPI><<<grid, R_THREADS, R_SMEM, st>>>(ma, mw, mr, my, im, a);
   return count_launch();
 }
 
