@@ -18,7 +18,6 @@ uses Python ``hash`` — process dependent, SURVEY.md gotcha 3; here blake2b).
 from __future__ import annotations
 
 import dataclasses
-import hashlib
 from typing import Optional
 
 import numpy as np
@@ -28,13 +27,42 @@ __all__ = ["EnsembleMember", "RecipeCore", "make_members", "fit_transform_all", 
 RECIPES = ("quantile_svd", "none")
 
 
+_FP_MULT = None
+
+
 def _fingerprint(X: np.ndarray) -> np.ndarray:
-    out = np.empty(X.shape[0], dtype=np.float32)
+    """Deterministic per-row fingerprint in [0, 1): a multiplicative hash of the row's float32 bit patterns
+    (vectorised: one pass over the table; the reference hashes row by row with Python ``hash``, which is
+    process dependent — SURVEY.md gotcha 3)."""
+    global _FP_MULT
     Xc = np.ascontiguousarray(X, dtype=np.float32)
-    for i in range(Xc.shape[0]):
-        h = hashlib.blake2b(Xc[i].tobytes(), digest_size=8).digest()
-        out[i] = (int.from_bytes(h, "little") % (1 << 24)) / float(1 << 24)
-    return out
+    w = Xc.view(np.uint32).astype(np.uint64)
+    if _FP_MULT is None or len(_FP_MULT) < w.shape[1]:
+        _FP_MULT = (np.random.default_rng(0x5EED).integers(1, 2**62, size=max(64, w.shape[1]), dtype=np.uint64) | np.uint64(1))
+    with np.errstate(over="ignore"):
+        h = (w * _FP_MULT[: w.shape[1]]).sum(axis=1, dtype=np.uint64)
+        h ^= h >> np.uint64(33)
+        h *= np.uint64(0xFF51AFD7ED558CCD)
+        h ^= h >> np.uint64(33)
+    return ((h >> np.uint64(40)).astype(np.float64) / float(1 << 24)).astype(np.float32)
+
+
+def _quantile_uniform(Xn: np.ndarray, quantiles: np.ndarray, references: np.ndarray) -> np.ndarray:
+    """Uniform-output quantile transform from fitted quantiles — the arithmetic of sklearn's
+    ``QuantileTransformer._transform_col`` (forward/backward interpolation averaged, bounds clipped, NaN
+    kept) without the estimator plumbing, which costs more than the interpolation at 300 rows."""
+    out = np.empty(Xn.shape, dtype=np.float64)
+    r = references
+    for j in range(Xn.shape[1]):
+        x = Xn[:, j].astype(np.float64)
+        q = quantiles[:, j]
+        ok = ~np.isnan(x)
+        res = x.copy()
+        res[ok] = 0.5 * (np.interp(x[ok], q, r) - np.interp(-x[ok], -q[::-1], -r[::-1]))
+        res[x + 1e-7 > q[-1]] = 1.0
+        res[x - 1e-7 < q[0]] = 0.0
+        out[:, j] = res
+    return out.astype(np.float32)
 
 
 class RecipeCore:
@@ -49,6 +77,7 @@ class RecipeCore:
         self._svd = None
         self._svd_mean = None
         self._svd_scale = None
+        self._q = self._r = self._basis = None
         self.fitted = False
 
     def features(self, X: np.ndarray, fit: bool) -> np.ndarray:
@@ -68,7 +97,9 @@ class RecipeCore:
                     self._qt = QuantileTransformer(n_quantiles=max(min(n // 10, 1000), 2),
                                                    output_distribution="uniform", random_state=0)
                     self._qt.fit(Xn)
-                parts.append(self._qt.transform(Xn).astype(np.float32))
+                    self._q = np.asarray(self._qt.quantiles_, dtype=np.float64)
+                    self._r = np.asarray(self._qt.references_, dtype=np.float64)
+                parts.append(_quantile_uniform(Xn, self._q, self._r))
             k = max(1, min(n // 10 + 1, F // 2)) if fit else self._svd.n_components
             Xz = np.nan_to_num(np.concatenate(parts, 1), nan=0.0, posinf=0.0, neginf=0.0)
             if fit:
@@ -76,7 +107,9 @@ class RecipeCore:
                 self._svd_scale = Xz.std(0) + 1e-6
                 self._svd = TruncatedSVD(n_components=k, algorithm="arpack", random_state=0)
                 self._svd.fit((Xz - self._svd_mean) / self._svd_scale)
-            parts.append(self._svd.transform((Xz - self._svd_mean) / self._svd_scale).astype(np.float32))
+                self._basis = np.asarray(self._svd.components_, dtype=np.float64).T.copy()
+            # TruncatedSVD.transform is X @ components_.T
+            parts.append((((Xz - self._svd_mean) / self._svd_scale).astype(np.float64) @ self._basis).astype(np.float32))
         if fit:
             self.fitted = True
         return np.concatenate(parts, 1)
