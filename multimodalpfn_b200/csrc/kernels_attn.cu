@@ -47,6 +47,7 @@ struct AttnCfg {
 struct AttnArgs {
   uint16_t* out;
   int T, n_q, n_kv, shared_kv, q_tiles;
+  int stack_rows;   // > 0: the six query heads of a (b, t) column are stacked on the tile's row axis, Sq_pad rows each
 };
 
 // DBG != 0: knock-out timing experiments (results are wrong): 1 no exp, 2 no S load from TMEM,
@@ -146,10 +147,13 @@ __global__ void __launch_bounds__(A_THREADS, AttnCfg<BK, PT>::kMinCtas)
   uint32_t* tmem_slot = (uint32_t*)(bars + 17);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int plane = blockIdx.x / p.q_tiles;     // (b*T + t)*kH + h; q tiles of a plane are adjacent CTAs
+  // Train pass: plane = (b*T + t)*kH + h, q tiles of a plane are adjacent CTAs.  Test pass (all six query
+  // heads read the head-0 K/V of their column, multi_head_attention.py:436-445): the heads are stacked on
+  // the row axis — row = h * Sq_pad + s of column bt — so that 6 x 300 rows fill 15 tiles instead of 18.
+  const int plane = blockIdx.x / p.q_tiles;
   const int q0 = (blockIdx.x % p.q_tiles) * A_BQ;
-  const int h = plane % kH;
-  const int bt = plane / kH;
+  const int h = p.stack_rows ? 0 : plane % kH;
+  const int bt = p.stack_rows ? plane : plane / kH;
   const int kv_plane = p.shared_kv ? bt : plane;
   const int nkt = (p.n_kv + BK - 1) / BK;
 
@@ -439,11 +443,15 @@ __global__ void __launch_bounds__(A_THREADS, AttnCfg<BK, PT>::kMinCtas)
     tc_fence_after();
     tmem_ld32(tmem_o + lane_off, v);
     tmem_ld_wait();
-    const int qi = q0 + r;
+    int qi = q0 + r, hh = h;
+    if (p.stack_rows) {
+      hh = qi / p.stack_rows;
+      qi = hh < kH ? qi - hh * p.stack_rows : p.n_q;      // rows past the last head: nothing to store
+    }
     if (qi < p.n_q) {
       const float inv = 1.0f / l_run;
       const int b = bt / p.T, t = bt % p.T;
-      uint16_t* dst = p.out + (((long long)b * p.n_q + qi) * p.T + t) * kE + h * kD;
+      uint16_t* dst = p.out + (((long long)b * p.n_q + qi) * p.T + t) * kE + hh * kD;
       uint4* d4 = reinterpret_cast<uint4*>(dst);
 #pragma unroll
       for (int i = 0; i < 4; ++i)
@@ -477,12 +485,17 @@ template <int BK, bool PT>
 int launch_attn_bk(const TcItemAttn& p, int poly, int dbg, cudaStream_t st) {
   const long long planes_q = (long long)p.B * p.T * kH;
   const long long planes_kv = p.shared_kv ? (long long)p.B * p.T : planes_q;
-  const int q_tiles = (p.n_q + A_BQ - 1) / A_BQ;
-  if (planes_q * q_tiles > 2147483647LL) { set_error("item attention: grid too large"); return MMPFN_EUNSUPPORTED; }
+  // stacking pays when it saves tiles; the rows between n_q and Sq_pad of every head are then computed
+  // (and dropped), so they should hold finite values (the QKV projection writes zeros there)
+  const bool stack = p.shared_kv && (kH * p.Sq_pad + A_BQ - 1) / A_BQ < kH * ((p.n_q + A_BQ - 1) / A_BQ);
+  const int q_tiles = stack ? (kH * p.Sq_pad + A_BQ - 1) / A_BQ : (p.n_q + A_BQ - 1) / A_BQ;
+  const long long grid_planes = stack ? planes_kv : planes_q;
+  if (grid_planes * q_tiles > 2147483647LL) { set_error("item attention: grid too large"); return MMPFN_EUNSUPPORTED; }
   CUtensorMap mq, mk, mvt;
   {
-    const cuuint64_t dims[3] = {(cuuint64_t)kD, (cuuint64_t)p.n_q, (cuuint64_t)planes_q};
-    const cuuint64_t strides[2] = {(cuuint64_t)kD * 2, (cuuint64_t)p.Sq_pad * kD * 2};
+    const cuuint64_t dims[3] = {(cuuint64_t)kD, (cuuint64_t)(stack ? kH * p.Sq_pad : p.n_q),
+                                (cuuint64_t)(stack ? planes_kv : planes_q)};
+    const cuuint64_t strides[2] = {(cuuint64_t)kD * 2, (cuuint64_t)(stack ? kH : 1) * p.Sq_pad * kD * 2};
     const cuuint32_t box[3] = {kD, A_BQ, 1};
     MMPFN_TRY(encode_map(&mq, p.q, 3, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_64B));
   }
@@ -498,8 +511,8 @@ int launch_attn_bk(const TcItemAttn& p, int poly, int dbg, cudaStream_t st) {
     const cuuint32_t box[3] = {64, kD, 1};
     MMPFN_TRY(encode_map(&mvt, p.vt, 3, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_128B));
   }
-  AttnArgs a{p.out, p.T, p.n_q, p.n_kv, p.shared_kv, q_tiles};
-  const dim3 grid((unsigned)(planes_q * q_tiles));
+  AttnArgs a{p.out, p.T, p.n_q, p.n_kv, p.shared_kv, q_tiles, stack ? p.Sq_pad : 0};
+  const dim3 grid((unsigned)(grid_planes * q_tiles));
   if (dbg) {
     switch (dbg) {
       case 1: launch_attn_t<BK, 0, 1, PT>(mq, mk, mvt, a, grid, st); break;

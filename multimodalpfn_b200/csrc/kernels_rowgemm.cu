@@ -296,8 +296,8 @@ __global__ void __launch_bounds__(R_THREADS, 1) tc_rowgemm_kernel(const __grid_c
       } else {  // TC_EPI_QKV_ITEMS: n-tile jn in {q,k,v}; 32-column chunk = head
         // Every head's [128 rows x 32] block goes through an 8 KB staging block and out by TMA: q and k
         // as [128][64 B] rows (64B swizzle) into their plane, v transposed ([32 d][128 s], two 128B-
-        // swizzled 64-column blocks) so that P V is a K-major x K-major MMA.  Rows past S are clipped by
-        // the tensor maps.  Head 0 of k and v is stored a second time into the layer's context.
+        // swizzled 64-column blocks) so that P V is a K-major x K-major MMA.  Rows past S_pad (v: columns past
+        // S) are clipped by the tensor maps.  Head 0 of k and v is stored a second time into the layer's context.
         const int per_b = p.T * p.tiles_s;
         const int tb = mt / per_b, rem = mt % per_b;
         const int tt = rem / p.tiles_s, s0 = (rem % p.tiles_s) * R_BM;
@@ -444,8 +444,10 @@ int launch_tc_rowgemm(const TcGemm& p, cudaStream_t st) {
   im.q = im.k = im.vt = im.k0 = im.vt0 = mw;
   if (p.epi == TC_EPI_QKV_ITEMS) {
     const cuuint64_t planes = (cuuint64_t)p.B * p.T * kH, planes0 = (cuuint64_t)p.B * p.T;
-    auto rows_map = [&](CUtensorMap* m, const void* base, cuuint64_t np) {      // [plane][S (pitch S_pad)][32]
-      const cuuint64_t dims[3] = {(cuuint64_t)kD, (cuuint64_t)p.S, np};
+    // rows S .. S_pad-1 of a plane receive zeros (their A rows are out of bounds = zero filled): the test
+    // pass of the item attention stacks the heads of a column and runs over those rows too
+    auto rows_map = [&](CUtensorMap* m, const void* base, cuuint64_t np) {      // [plane][S_pad][32]
+      const cuuint64_t dims[3] = {(cuuint64_t)kD, (cuuint64_t)p.S_pad, np};
       const cuuint64_t strides[2] = {(cuuint64_t)kD * 2, (cuuint64_t)p.S_pad * kD * 2};
       const cuuint32_t box[3] = {kD, R_BM, 1};
       return encode_map(m, base, 3, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_64B);
