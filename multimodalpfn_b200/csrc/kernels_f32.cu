@@ -292,32 +292,51 @@ __device__ __forceinline__ void mma_bf16(float (&d)[4], const uint32_t (&a)[4], 
                : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
 }
 
-// KT = number of 16-key tiles the register file is sized for (T <= 16*KT)
+// KT = number of 16-key tiles the register file is sized for (T <= 16*KT).
+// A CTA walks table rows blockIdx.x, blockIdx.x + gridDim.x, ... with two staging buffers: the qkv block
+// of the next row streams in (cp.async) while the current row is computed, so the DRAM latency of a row is
+// paid under the previous row's arithmetic instead of once per CTA.
 template <int KT>
 __global__ void __launch_bounds__(384) feat_attn_mma_kernel(const uint16_t* __restrict__ qkv,
-                                                            uint16_t* __restrict__ att, int T) {
+                                                            uint16_t* __restrict__ att, int T, long long n_rows) {
   extern __shared__ __align__(16) uint8_t fsm[];
-  const long long row = blockIdx.x;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int n_kt = (T + 15) >> 4;               // 16-key tiles actually present
   const int Tp = n_kt * 16;
-  const uint32_t sbase = (uint32_t)__cvta_generic_to_shared(fsm);
-
-  // stage [T][576] bf16 -> smem rows of FA_ROW_BYTES; zero the padded token rows
-  const uint8_t* src = reinterpret_cast<const uint8_t*>(qkv + row * T * (3 * kE));
+  const uint32_t buf_bytes = (uint32_t)Tp * FA_ROW_BYTES;
+  const uint32_t sbase0 = (uint32_t)__cvta_generic_to_shared(fsm);
   constexpr int CH = 3 * kE * 2 / 16;           // 72 chunks of 16 B per token
-  for (int i = threadIdx.x; i < T * CH; i += blockDim.x) {
-    const int t = i / CH, c = i % CH;
-    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(sbase + t * FA_ROW_BYTES + c * 16),
-                 "l"(src + (long long)t * (3 * kE * 2) + c * 16));
+
+  // stage [T][576] bf16 of one table row -> smem rows of FA_ROW_BYTES
+  auto stage = [&](long long row, int b) {
+    const uint8_t* src = reinterpret_cast<const uint8_t*>(qkv + row * T * (3 * kE));
+    const uint32_t dst = sbase0 + b * buf_bytes;
+    for (int i = threadIdx.x; i < T * CH; i += blockDim.x) {
+      const int t = i / CH, c = i % CH;
+      asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst + t * FA_ROW_BYTES + c * 16),
+                   "l"(src + (long long)t * (3 * kE * 2) + c * 16));
+    }
+    asm volatile("cp.async.commit_group;");
+  };
+  // the padded token rows of both buffers stay zero for the CTA's whole life
+  for (int b = 0; b < 2; ++b)
+    for (int i = threadIdx.x; i < (Tp - T) * CH; i += blockDim.x) {
+      const int t = T + i / CH, c = i % CH;
+      *reinterpret_cast<uint4*>(fsm + b * buf_bytes + t * FA_ROW_BYTES + c * 16) = make_uint4(0, 0, 0, 0);
+    }
+  long long row = blockIdx.x;
+  if (row < n_rows) stage(row, 0);
+  for (int it = 0; row < n_rows; row += gridDim.x, ++it) {
+  const int cur = it & 1;
+  const long long nxt = row + gridDim.x;
+  if (nxt < n_rows) {
+    stage(nxt, cur ^ 1);                         // (its previous reader finished before the barrier below)
+    asm volatile("cp.async.wait_group 1;");
+  } else {
+    asm volatile("cp.async.wait_group 0;");
   }
-  for (int i = threadIdx.x; i < (Tp - T) * CH; i += blockDim.x) {
-    const int t = T + i / CH, c = i % CH;
-    *reinterpret_cast<uint4*>(fsm + t * FA_ROW_BYTES + c * 16) = make_uint4(0, 0, 0, 0);
-  }
-  asm volatile("cp.async.commit_group;");
-  asm volatile("cp.async.wait_group 0;");
   __syncthreads();
+  const uint32_t sbase = sbase0 + cur * buf_bytes;
 
   const float c2 = 0.17677669529663687f * 1.4426950408889634f;   // log2(e)/sqrt(d)
   const int n_items = kH * n_kt;
@@ -407,21 +426,33 @@ __global__ void __launch_bounds__(384) feat_attn_mma_kernel(const uint16_t* __re
       if (q1 < T) *reinterpret_cast<uint32_t*>(o1 + nt * 8) = pack_bf16x2(oacc[nt][2] * i1, oacc[nt][3] * i1);
     }
   }
+  __syncthreads();                               // everyone is done with this buffer before it is refilled
+  }
 }
 
 template <int KT>
 int launch_feat_attn_mma_t(const uint16_t* qkv, uint16_t* att, long long n_seq, int T, cudaStream_t st) {
   const int Tp = (T + 15) / 16 * 16;
-  const size_t smem = (size_t)Tp * FA_ROW_BYTES;
+  const size_t smem = (size_t)2 * Tp * FA_ROW_BYTES;
   auto kern = feat_attn_mma_kernel<KT>;
   static bool configured = false;
+  static int n_sm = 148;
   if (!configured) {
-    cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, KT * 16 * FA_ROW_BYTES);
+    cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * KT * 16 * FA_ROW_BYTES);
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev);
     configured = true;
   }
   const int n_items = kH * (Tp / 16);
   const int warps = n_items < 12 ? n_items : 12;
-  kern<<<(unsigned)n_seq, warps * 32, smem, st>>>(qkv, att, T);
+  // CTAs resident per SM: shared memory (two staging buffers each) and 2048 threads
+  int per_sm = (int)((227 * 1024) / (smem + 1024));
+  if (per_sm > 2048 / (warps * 32)) per_sm = 2048 / (warps * 32);
+  if (per_sm < 1) per_sm = 1;
+  long long grid = (long long)n_sm * per_sm;
+  if (grid > n_seq) grid = n_seq;
+  kern<<<(unsigned)grid, warps * 32, smem, st>>>(qkv, att, T, n_seq);
   return count_launch();
 }
 }  // namespace
