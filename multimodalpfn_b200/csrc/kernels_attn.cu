@@ -550,7 +550,7 @@ int launch_tc_item_attn(const TcItemAttn& p, cudaStream_t st) {
     e = getenv("MMPFN_ATTN_PT");          // 0: P through shared memory (the older hand-off), A/B timing only
     pt = e ? atoi(e) : 1;
   }
-  if (bk == 112) return launch_attn_bk<112, false>(p, poly, dbg, st);
+  if (bk == 112) return pt ? launch_attn_bk<112, true>(p, poly, dbg, st) : launch_attn_bk<112, false>(p, poly, dbg, st);
   if (!pt) return launch_attn_bk<48, false>(p, poly, dbg, st);
   return launch_attn_bk<48, true>(p, poly, dbg, st);
 }
