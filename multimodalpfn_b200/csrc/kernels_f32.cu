@@ -298,7 +298,8 @@ __device__ __forceinline__ void mma_bf16(float (&d)[4], const uint32_t (&a)[4], 
 // paid under the previous row's arithmetic instead of once per CTA.
 template <int KT>
 __global__ void __launch_bounds__(384) feat_attn_mma_kernel(const uint16_t* __restrict__ qkv,
-                                                            uint16_t* __restrict__ att, int T, long long n_rows) {
+                                                            uint16_t* __restrict__ att, int T, long long n_rows,
+                                                            int n_buf) {
   extern __shared__ __align__(16) uint8_t fsm[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int n_kt = (T + 15) >> 4;               // 16-key tiles actually present
@@ -318,8 +319,9 @@ __global__ void __launch_bounds__(384) feat_attn_mma_kernel(const uint16_t* __re
     }
     asm volatile("cp.async.commit_group;");
   };
-  // the padded token rows of both buffers stay zero for the CTA's whole life
-  for (int b = 0; b < 2; ++b)
+  // the padded token rows of the buffers stay zero for the CTA's whole life.  n_buf = 1 (wide rows: two
+  // buffers would not fit shared memory): load, compute, load, ... without the overlap.
+  for (int b = 0; b < n_buf; ++b)
     for (int i = threadIdx.x; i < (Tp - T) * CH; i += blockDim.x) {
       const int t = T + i / CH, c = i % CH;
       *reinterpret_cast<uint4*>(fsm + b * buf_bytes + t * FA_ROW_BYTES + c * 16) = make_uint4(0, 0, 0, 0);
@@ -327,9 +329,9 @@ __global__ void __launch_bounds__(384) feat_attn_mma_kernel(const uint16_t* __re
   long long row = blockIdx.x;
   if (row < n_rows) stage(row, 0);
   for (int it = 0; row < n_rows; row += gridDim.x, ++it) {
-  const int cur = it & 1;
+  const int cur = n_buf == 2 ? (it & 1) : 0;
   const long long nxt = row + gridDim.x;
-  if (nxt < n_rows) {
+  if (n_buf == 2 && nxt < n_rows) {
     stage(nxt, cur ^ 1);                         // (its previous reader finished before the barrier below)
     asm volatile("cp.async.wait_group 1;");
   } else {
@@ -427,18 +429,20 @@ __global__ void __launch_bounds__(384) feat_attn_mma_kernel(const uint16_t* __re
     }
   }
   __syncthreads();                               // everyone is done with this buffer before it is refilled
+  if (n_buf == 1 && nxt < n_rows) stage(nxt, 0);
   }
 }
 
 template <int KT>
 int launch_feat_attn_mma_t(const uint16_t* qkv, uint16_t* att, long long n_seq, int T, cudaStream_t st) {
   const int Tp = (T + 15) / 16 * 16;
-  const size_t smem = (size_t)2 * Tp * FA_ROW_BYTES;
+  const int n_buf = (size_t)2 * Tp * FA_ROW_BYTES <= 200 * 1024 ? 2 : 1;
+  const size_t smem = (size_t)n_buf * Tp * FA_ROW_BYTES;
   auto kern = feat_attn_mma_kernel<KT>;
   static bool configured = false;
   static int n_sm = 148;
   if (!configured) {
-    cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 2 * KT * 16 * FA_ROW_BYTES);
+    cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
     int dev = 0;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev);
@@ -452,7 +456,7 @@ int launch_feat_attn_mma_t(const uint16_t* qkv, uint16_t* att, long long n_seq, 
   if (per_sm < 1) per_sm = 1;
   long long grid = (long long)n_sm * per_sm;
   if (grid > n_seq) grid = n_seq;
-  kern<<<(unsigned)grid, warps * 32, smem, st>>>(qkv, att, T, n_seq);
+  kern<<<(unsigned)grid, warps * 32, smem, st>>>(qkv, att, T, n_seq, n_buf);
   return count_launch();
 }
 }  // namespace

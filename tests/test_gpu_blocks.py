@@ -217,3 +217,37 @@ def test_single_layer_vs_oracle(precision, tol, B, S, T, n_test):
         assert e1 < tol and e2 < tol, (e1, e2)
         if precision == "bf16":
             assert (stb[b].float().cpu() - ref_tr).abs().max().item() < tol + 0.03
+
+
+@pytest.mark.parametrize("seed", list(range(10)))
+def test_single_layer_random_shapes(seed):
+    """layers_train + layers_test at random ragged shapes (1-700 rows, 2-140 tokens, 1-3 estimators): tiles
+    that are mostly padding, key sets shorter than one 48-key tile, token counts that switch the feature
+    attention between its register-tile sizes — bf16 path vs the oracle's layer_forward."""
+    from oracle import forward_ref as R
+    rng = np.random.default_rng(1000 + seed)
+    B = int(rng.integers(1, 4))
+    S = int(rng.choice([1, 2, 37, 47, 48, 49, 127, 128, 129, 300, 511, 700]))
+    T = int(rng.choice([2, 3, 9, 16, 17, 33, 65, 100, 140]))
+    n_test = int(rng.choice([1, 5, 44, 128, 131, 300]))
+    if B * S * T > 60000:
+        B = 1
+    model, sd, geom = _one_layer_model("bf16", seed=seed)
+    tsd = R.as_torch_state_dict(sd)
+    g = torch.Generator().manual_seed(seed)
+    tr = torch.randn(B, S, T, 192, generator=g)
+    te = torch.randn(B, n_test, T, 192, generator=g)
+    st, se = tr.cuda().contiguous(), te.cuda().contiguous()
+    stb, seb = st.to(torch.bfloat16), se.to(torch.bfloat16)
+    kv = model.alloc_kv(B, S, T)
+    model.layers_train(st, stb, kv)
+    model.layers_test(se, seb, kv, S)
+    torch.cuda.synchronize()
+    assert torch.isfinite(st).all() and torch.isfinite(se).all()
+    for b in range(B):
+        ref_tr, kvr = R.layer_forward(tr[b], S, tsd, 0, want_kv=True)
+        ref_te, _ = R.layer_forward(te[b], 0, tsd, 0, kv_in=kvr)
+        e1 = (st[b].cpu() - ref_tr).abs().max().item()
+        e2 = (se[b].cpu() - ref_te).abs().max().item()
+        assert e1 < 0.06 and e2 < 0.06, (B, S, T, n_test, e1, e2)
+        assert (stb[b].float().cpu() - ref_tr).abs().max().item() < 0.09
