@@ -155,3 +155,31 @@ def test_pad_ufes_shape_vs_oracle(precision):
     srt = np.sort(pr, 1)
     decided = (srt[:, -1] - srt[:, -2]) > 4 * P_TOL[precision]
     assert (p.argmax(1)[decided] == pr.argmax(1)[decided]).all()
+
+
+@pytest.mark.parametrize("seed", list(range(8)))
+def test_model_random_configs_vs_oracle(seed):
+    """Random small problems — mixer type, MGM/CAP head counts, embeddings per row, feature count (odd too),
+    class count, train/test split, a few NaN cells — CUDA path (fp32 and bf16) vs the oracle."""
+    from multimodalpfn_b200.synth import Geometry, make_state_dict
+    rng = np.random.default_rng(500 + seed)
+    mixer = ["MGM+CAP", "MGM", "MoE", "MGM+CAP"][seed % 4]
+    mgm = int(rng.integers(1, 5))
+    cap = int(rng.choice([1, 2, 4, 8])) if mixer != "MGM" else None
+    geom = Geometry(mgm_heads=mgm, cap_heads=cap, mixer_type=mixer, nlayers=2)
+    sd = make_state_dict(geom, seed=seed)
+    n_tr, n_te = int(rng.integers(20, 200)), int(rng.integers(1, 150))
+    F, n_tok, n_cls = int(rng.integers(1, 24)), int(rng.integers(1, 4)), int(rng.integers(2, 11))
+    S = n_tr + n_te
+    X = rng.standard_normal((S, F)).astype(np.float32) * rng.uniform(0.1, 30, size=F).astype(np.float32)
+    X[rng.random((S, F)) < 0.02] = np.nan
+    X[:, 0] = np.where(np.isnan(X[:, 0]), 0.0, X[:, 0])          # keep one fully observed column
+    img = rng.standard_normal((S, n_tok, 768)).astype(np.float32)
+    y = rng.integers(0, n_cls, size=n_tr).astype(np.float32)
+    y[:n_cls] = np.arange(n_cls)                                  # every class present
+    ref = R.forward_joint(t(X), t(img), t(y), R.as_torch_state_dict(sd), geom, seed=0).numpy()
+    for precision in ("fp32", "bf16"):
+        model = B200PerFeatureTransformer(sd, geom, precision=precision, seed=0)
+        logits = _run_joint(model, X, img, y)
+        p, pr = softmax_np(logits[:, :n_cls] / 0.9), softmax_np(ref[:, :n_cls] / 0.9)
+        assert np.abs(p - pr).max() <= P_TOL[precision], (precision, mixer, mgm, cap, n_tr, n_te, F, n_tok, n_cls)
