@@ -188,27 +188,34 @@ __global__ void __launch_bounds__(kE) stem_tokens_kernel(
     if (outb) st_bf16(outb + (long long)t * kE + e, v);
     bad |= isnan(v);
   };
-  // tabular groups: transform (encoders.py:480-493, :761-780, :639-655) + Linear(2*fpg -> E) (:422-425)
+  // tabular groups: transform (encoders.py:480-493, :761-780, :639-655) + Linear(2*fpg -> E) (:422-425).
+  // The per-cell transform (NaN/inf fill, soft clip with its logarithms, z-norm) is the same for all 192
+  // embedding columns: one thread per cell computes (value, indicator) into shared memory, then every
+  // thread only does the 2*fpg FMAs of its column.
   if (G > 0) {
+    __shared__ float cell_v[1024], cell_i[1024];                 // G * fpg <= 1024 cells per row (checked on launch)
+    for (int slot = e; slot < G * fpg; slot += kE) {
+      const int col = (int)st[L.src() + slot];
+      float v = 0.f, ind = 0.f;
+      if (col >= 0) {
+        const float raw = x[b * x_bstride + s * F + col];
+        ind = isnan(raw) ? -2.0f : (isinf(raw) ? (raw > 0 ? 2.0f : 4.0f) : 0.0f);
+        float t1 = fill_bad(raw, st[L.fill() + slot]);
+        t1 = soft_clip(t1, st[L.lo() + slot], st[L.hi() + slot]);
+        t1 = clip100((t1 - st[L.mean() + slot]) / st[L.stdv() + slot]);
+        v = t1 * st[L.scale() + slot / fpg];
+      }
+      cell_v[slot] = v;
+      cell_i[slot] = ind;
+    }
+    __syncthreads();
     float we[8];
     for (int j = 0; j < 2 * fpg; ++j) we[j] = enc_w[e * 2 * fpg + j];
     for (int g = 0; g < G; ++g) {
       float acc = 0.f;
-      const float sc = st[L.scale() + g];
       for (int j = 0; j < fpg; ++j) {
-        const int slot = g * fpg + j;
-        const int col = (int)st[L.src() + slot];
-        float v = 0.f, ind = 0.f;
-        if (col >= 0) {
-          const float raw = x[b * x_bstride + s * F + col];
-          ind = isnan(raw) ? -2.0f : (isinf(raw) ? (raw > 0 ? 2.0f : 4.0f) : 0.0f);
-          float t1 = fill_bad(raw, st[L.fill() + slot]);
-          t1 = soft_clip(t1, st[L.lo() + slot], st[L.hi() + slot]);
-          t1 = clip100((t1 - st[L.mean() + slot]) / st[L.stdv() + slot]);
-          v = t1 * sc;
-        }
-        acc = fmaf(v, we[j], acc);
-        acc = fmaf(ind, we[fpg + j], acc);
+        acc = fmaf(cell_v[g * fpg + j], we[j], acc);
+        acc = fmaf(cell_i[g * fpg + j], we[fpg + j], acc);
       }
       emit(g, acc + pos_emb[g * kE + e]);
     }
@@ -380,6 +387,7 @@ int launch_stem_tokens(const mmpfn_geometry* g, const mmpfn_weights* w, const fl
   const int fpg = g->features_per_group;
   const int G = x ? (F + fpg - 1) / fpg : 0;
   if (fpg > 4) { set_error("features_per_group %d > 4", fpg); return MMPFN_EUNSUPPORTED; }
+  if (G * fpg > 1024) { set_error("stem_tokens: %d feature cells per row exceed the 1024 the kernel stages", G * fpg); return MMPFN_EUNSUPPORTED; }
   stem_tokens_kernel<<<dim3(S, B), kE, 0, st>>>(x, stats, img_tok, y, y_mean, y_mask, pos_emb, w->enc_w, w->yenc_w,
                                                w->yenc_b, S, F, fpg, G, H_img, x_bstride, y_bstride, img_bstride, state_f32, state_bf16,
                                                nan_flag);
