@@ -2,18 +2,22 @@
 // flash-attention kernel written directly against sm_100a, d = 32:
 //
 //   S = Q K^T and O += P V on tcgen05 (accumulators in TMEM, operands staged by TMA), online softmax
-//   in fp32 by four warps (thread = query row), P handed to the second MMA through a 128B-swizzled
-//   shared-memory tile.
+//   in fp32 by four warps (thread = query row).  P goes back into tensor memory over the S columns it
+//   came from (bf16 pairs) and the second MMA reads its A operand there (PT = true, the default); the
+//   older hand-off through a 128B-swizzled shared-memory tile is kept as PT = false for A/B timing.
 //
 // At d = 32 every exponential buys only 128 tensor FLOP, so the kernel lives on the MUFU/FMA pipes
 // (16 ex2/clk/SM = 595 TFLOP/s at 1965 MHz), not on the tensor pipe: everything here is arranged so
-// that the softmax warps never wait (S double buffered in TMEM, lazy row maximum, per-parity
-// barriers) and that enough of them are resident to keep the MUFU queue full.
+// that the softmax warps never wait (S double buffered in TMEM, no row maximum in the inner loop,
+// per-parity barriers) and that enough of them are resident to keep the MUFU queue full.
 //
 // Two tile shapes (template BK = keys per tile):
-//   BK = 112, 2 CTAs/SM   TMEM: S0 [0,112) S1 [112,224) O [224,256)
-//   BK = 48,  4 CTAs/SM   TMEM: S0 [0,48)  S1 [48,96)   O [96,128)   — twice the resident softmax
-//                         warps (4 per scheduler) for latency hiding
+//   BK = 48,  4 CTAs/SM   TMEM: S0 [0,48)  S1 [48,96)   O [96,128)   — the default: four softmax warps
+//                         per scheduler (460 TFLOP/s at the cfg2 train shape)
+//   BK = 112, 2 CTAs/SM   TMEM: S0 [0,112) S1 [112,224) O [224,256)  — MMPFN_ATTN_BK=112 (411 TFLOP/s)
+//
+// Test pass (every query head of a column reads that column's head-0 K/V): the six heads are stacked on
+// the tile's row axis, so 6 x 300 query rows fill 15 tiles of 128 instead of 18.
 //
 // Every mbarrier wait is bounded (trap after ~2 s) so that a protocol bug cannot hang the GPU.
 #include "tc_common.cuh"

@@ -31,10 +31,11 @@ fn.argtypes = [C.c_void_p, C.c_int]
 fn.restype = C.c_int
 assert fn(buf.ctypes.data, 4096) == 0
 t0 = buf[0]
-nkt = (n + 111) // 112
-print("softmax thread 0: per tile [start, s_full ok, S in regs+s_free, max done, exp+P done, pv_done ok, rescale done, p_full arrived] (cycles from CTA's first stamp)")
+BK = int(os.environ.get("MMPFN_ATTN_BK", "48"))
+nkt = min((n + BK - 1) // BK, 40)
+print("softmax thread 0: per tile [loop top, s_full ok, S in regs, first-tile max done, sweep + P stored, -, rescale done, p_full arrived] (cycles from the CTA's first stamp; slot 5 is unused)")
 for j in range(nkt):
     print(j, [int(x - t0) for x in buf[j * 8:j * 8 + 8]], "tile", int(buf[j * 8 + 7] - buf[j * 8]))
-print("mma thread: per tile [s_free ok, S(j+2) issued, p_full ok, PV issued+committed]")
+print("mma thread: per tile [-, -, p_full ok, PV (+ S(j+2)) issued and committed]  (slots 0-1 only with P through shared memory)")
 for j in range(nkt):
     print(j, [int(x - t0) if x else None for x in buf[2048 + j * 4:2048 + j * 4 + 4]])
