@@ -419,13 +419,29 @@ __global__ void __launch_bounds__(384) feat_attn_mma_kernel(const uint16_t* __re
     l1 += __shfl_xor_sync(0xffffffffu, l1, 1);
     l1 += __shfl_xor_sync(0xffffffffu, l1, 2);
     const float i0 = 1.0f / l0, i1 = 1.0f / l1;
+    // The output block of this item overwrites the item's own Q block in shared memory (16 tokens x 64 B
+    // that only this warp read, and it holds them in registers since the first ldmatrix): the row then
+    // leaves as whole 16-byte pieces, coalesced, instead of 4-byte stores scattered over 8 token rows.
     const int q0 = mt * 16 + (lane >> 2), q1 = q0 + 8;
-    uint16_t* o0 = att + (row * T + q0) * kE + h * kD + (lane & 3) * 2;
-    uint16_t* o1 = att + (row * T + q1) * kE + h * kD + (lane & 3) * 2;
+    const uint32_t so0 = sbase + q0 * FA_ROW_BYTES + (h * kD + (lane & 3) * 2) * 2;
+    const uint32_t so1 = sbase + q1 * FA_ROW_BYTES + (h * kD + (lane & 3) * 2) * 2;
+    __syncwarp();
 #pragma unroll
     for (int nt = 0; nt < 4; ++nt) {
-      if (q0 < T) *reinterpret_cast<uint32_t*>(o0 + nt * 8) = pack_bf16x2(oacc[nt][0] * i0, oacc[nt][1] * i0);
-      if (q1 < T) *reinterpret_cast<uint32_t*>(o1 + nt * 8) = pack_bf16x2(oacc[nt][2] * i1, oacc[nt][3] * i1);
+      asm volatile("st.shared.b32 [%0], %1;" ::"r"(so0 + nt * 16), "r"(pack_bf16x2(oacc[nt][0] * i0, oacc[nt][1] * i0)) : "memory");
+      asm volatile("st.shared.b32 [%0], %1;" ::"r"(so1 + nt * 16), "r"(pack_bf16x2(oacc[nt][2] * i1, oacc[nt][3] * i1)) : "memory");
+    }
+  }
+  __syncthreads();
+  {
+    constexpr int OC = kE * 2 / 16;               // 24 pieces of 16 B per token
+    uint8_t* dst = reinterpret_cast<uint8_t*>(att + row * T * kE);
+    for (int i = threadIdx.x; i < T * OC; i += blockDim.x) {
+      const int t = i / OC, c = i % OC;
+      uint4 v;
+      asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w)
+                   : "r"(sbase + t * FA_ROW_BYTES + c * 16));
+      *reinterpret_cast<uint4*>(dst + (long long)t * (kE * 2) + c * 16) = v;
     }
   }
   __syncthreads();                               // everyone is done with this buffer before it is refilled
