@@ -158,6 +158,24 @@ int mmpfn_layers_test(const mmpfn_geometry* g, const mmpfn_weights* w, float* st
                       int B, int S, int T, int n_train, int precision, const void* kv, void* workspace,
                       size_t workspace_bytes, void* stream);
 
+/* Several estimator groups ("segments": same row count S, own batch B and token count T) through the layers
+ * in one call, bf16 mode.  Their states are laid back to back in one buffer — segment i occupies
+ * B_i*S*T_i token rows of 192, in list order — so the sublayers that work on the flat token axis (QKV and
+ * output projections + LayerNorm, MLP) launch once for all segments; the attentions launch per segment.
+ * kv[i]: segment i's context (mmpfn_kv_bytes(B_i, n_train, T_i)); written by the train pass (may be NULL
+ * there), read by the test pass.  Same results as one mmpfn_layers_train / _test call per segment. */
+#define MMPFN_MAX_SEGMENTS 8
+typedef struct mmpfn_segment {
+  int32_t B, T;
+} mmpfn_segment;
+size_t mmpfn_layers_multi_ws_bytes(const mmpfn_geometry* g, const mmpfn_segment* segs, int n_seg, int S);
+int mmpfn_layers_train_multi(const mmpfn_geometry* g, const mmpfn_weights* w, float* state_f32, uint16_t* state_bf16,
+                             const mmpfn_segment* segs, int n_seg, int S, void* const* kv, void* workspace,
+                             size_t workspace_bytes, void* stream);
+int mmpfn_layers_test_multi(const mmpfn_geometry* g, const mmpfn_weights* w, float* state_f32, uint16_t* state_bf16,
+                            const mmpfn_segment* segs, int n_seg, int S, int n_train, void* const* kv, void* workspace,
+                            size_t workspace_bytes, void* stream);
+
 /* ---- decoder + probability tail ------------------------------------------------------------ */
 /* transformer.py:392-396, :850-853: logits[b][s][:] = W2 gelu(W1 state[b][s][T-1] + b1) + b2.
  * state [B][S][T][E] -> logits [B][S][n_out]; hidden scratch [B*S][nhid] fp32. */

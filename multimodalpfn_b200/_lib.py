@@ -32,7 +32,12 @@ class Weights(C.Structure):
     _fields_ = [(n, c_void_p) for n in WEIGHT_FIELDS]
 
 
+class Segment(C.Structure):
+    _fields_ = [("B", C.c_int32), ("T", C.c_int32)]
+
+
 PG, PW = C.POINTER(Geometry), C.POINTER(Weights)
+PS, PVP = C.POINTER(Segment), C.POINTER(C.c_void_p)
 
 # name -> (restype, argtypes): exactly the entry points include/mmpfn_b200.h declares
 SIGNATURES = {
@@ -50,6 +55,10 @@ SIGNATURES = {
                                   c_int, c_int, c_int, c_int, c_ll, c_ll, c_ll, c_void_p, c_void_p, c_void_p, c_void_p]),
     "mmpfn_layers_ws_bytes": (c_size_t, [PG, c_int, c_int, c_int, c_int]),
     "mmpfn_kv_bytes": (c_size_t, [PG, c_int, c_int, c_int, c_int]),
+    "mmpfn_layers_multi_ws_bytes": (c_size_t, [PG, PS, c_int, c_int]),
+    "mmpfn_layers_train_multi": (c_int, [PG, PW, c_void_p, c_void_p, PS, c_int, c_int, PVP, c_void_p, c_size_t, c_void_p]),
+    "mmpfn_layers_test_multi": (c_int, [PG, PW, c_void_p, c_void_p, PS, c_int, c_int, c_int, PVP, c_void_p, c_size_t,
+                                        c_void_p]),
     "mmpfn_layers_train": (c_int, [PG, PW, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p,
                                    c_size_t, c_void_p]),
     "mmpfn_layers_test": (c_int, [PG, PW, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p,

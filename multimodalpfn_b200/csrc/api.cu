@@ -477,6 +477,135 @@ int mmpfn_layers_test(const mmpfn_geometry* g, const mmpfn_weights* w, float* st
   return MMPFN_OK;
 }
 
+// ---- several estimator groups (segments) in one call -------------------------------------------------
+// Segments differ in their token count T (and batch B) but share the row count S.  Their states sit back
+// to back in ONE [M_total][192] buffer, so the sublayers that do not care about T — both QKV/output
+// projections on the flat token axis and the MLP — run as ONE launch over all segments (longer grids:
+// less tile-count rounding per launch, half the launches); only the two attentions and the item QKV
+// scatter, whose tiling follows T, launch per segment.
+struct SegWs {
+  uint16_t *qi, *ki, *vti;
+};
+struct MultiWs {
+  uint16_t *hid_b, *att_b;
+  SegWs seg[MMPFN_MAX_SEGMENTS];
+  size_t bytes;
+};
+static MultiWs carve_multi(void* base, const mmpfn_segment* segs, int n_seg, int S, long long M_total) {
+  MultiWs w{};
+  size_t off = 0;
+  auto take = [&](size_t bytes) {
+    char* p = base ? (char*)base + off : nullptr;
+    off += align_up(bytes, 1024);
+    return (uint16_t*)p;
+  };
+  w.hid_b = take((size_t)M_total * kHid * 2);      // also the feature-attention qkv block (never live together)
+  w.att_b = take((size_t)M_total * kE * 2);
+  for (int i = 0; i < n_seg; ++i) {
+    const size_t plane = (size_t)segs[i].B * segs[i].T * kH * kv_pad(S) * kD * 2;
+    w.seg[i].qi = take(plane);
+    w.seg[i].ki = take(plane);
+    w.seg[i].vti = take(plane);
+  }
+  w.bytes = off;
+  return w;
+}
+static int check_segments(const mmpfn_segment* segs, int n_seg, int S, long long* M_total) {
+  if (!segs || n_seg < 1 || n_seg > MMPFN_MAX_SEGMENTS || S < 1) { set_error("layers_multi: bad segment list"); return MMPFN_EINVAL; }
+  long long m = 0;
+  for (int i = 0; i < n_seg; ++i) {
+    if (segs[i].B < 1 || segs[i].T < 2) { set_error("layers_multi: bad segment %d (B %d T %d)", i, segs[i].B, segs[i].T); return MMPFN_EINVAL; }
+    m += (long long)segs[i].B * S * segs[i].T;
+  }
+  if (m > 2147483647LL) { set_error("layers_multi: too many tokens"); return MMPFN_EUNSUPPORTED; }
+  *M_total = m;
+  return MMPFN_OK;
+}
+
+size_t mmpfn_layers_multi_ws_bytes(const mmpfn_geometry* g, const mmpfn_segment* segs, int n_seg, int S) {
+  long long M = 0;
+  if (check_geometry(g) != MMPFN_OK || check_segments(segs, n_seg, S, &M) != MMPFN_OK) return 0;
+  return carve_multi(nullptr, segs, n_seg, S, M).bytes;
+}
+
+// train != 0: self-attention over the S rows, head-0 K/V written to kv[i] (may be NULL);
+// train == 0: the S rows are test rows attending to the n_train rows' context kv[i]
+static int layers_multi(const mmpfn_geometry* g, const mmpfn_weights* w, float* state, uint16_t* state_b,
+                        const mmpfn_segment* segs, int n_seg, int S, int n_train, int train, void* const* kv,
+                        void* workspace, size_t workspace_bytes, cudaStream_t st) {
+  MMPFN_TRY(check_geometry(g));
+  MMPFN_TRY(require_device());
+  long long M = 0;
+  MMPFN_TRY(check_segments(segs, n_seg, S, &M));
+  if (!w || !w->layers_f32 || !w->layers_bf16 || !state || !state_b || !kv) { set_error("layers_multi: null argument (bf16 mode only)"); return MMPFN_EINVAL; }
+  if (!train) for (int i = 0; i < n_seg; ++i) if (!kv[i] || n_train < 1) { set_error("layers_multi: the test pass needs every segment's context"); return MMPFN_EINVAL; }
+  MultiWs ws = carve_multi(workspace, segs, n_seg, S, M);
+  if (!workspace || workspace_bytes < ws.bytes) { set_error("layers_multi: workspace %zu < %zu bytes", workspace_bytes, ws.bytes); return MMPFN_EINVAL; }
+  const int Sp = kv_pad(S), Np = kv_pad(n_train);
+  LayerWs flat{};
+  flat.hid_b = ws.hid_b; flat.qkv_b = ws.hid_b; flat.att_b = ws.att_b;
+  for (int l = 0; l < g->nlayers; ++l) {
+    const LayerW lw = layer_w(w, l);
+    // features: QKV over all tokens, attention per segment (rows of T_i tokens), out-projection + LN over all
+    {
+      TcGemm a{};
+      a.A = state_b; a.W = lw.fqkv_b; a.M = (int)M; a.N = 3 * kE; a.K = kE; a.epi = TC_EPI_BF16; a.out_bf16 = ws.hid_b;
+      MMPFN_TRY(proj_gemm(a, st));
+      long long off = 0;
+      for (int i = 0; i < n_seg; ++i) {
+        MMPFN_TRY(launch_feat_attn_bf16(ws.hid_b + off * 3 * kE, ws.att_b + off * kE, (long long)segs[i].B * S, segs[i].T, st));
+        off += (long long)segs[i].B * S * segs[i].T;
+      }
+      TcGemm o{};
+      o.A = ws.att_b; o.W = lw.fout_b; o.M = (int)M; o.N = kE; o.K = kE; o.epi = TC_EPI_RESID_LN;
+      o.resid_f32 = state; o.ln_bf16 = state_b;
+      MMPFN_TRY(proj_gemm(o, st));
+    }
+    // items: QKV scatter + attention per segment (tiles follow T_i), out-projection + LN over all
+    {
+      long long off = 0;
+      for (int i = 0; i < n_seg; ++i) {
+        const int B = segs[i].B, T = segs[i].T;
+        TcGemm q{};
+        q.A = state_b + off * kE; q.W = lw.iqkv_b; q.N = train ? 3 * kE : kE; q.K = kE; q.items = 1; q.B = B; q.S = S; q.T = T;
+        q.epi = TC_EPI_QKV_ITEMS; q.q_out = ws.seg[i].qi; q.S_pad = Sp;
+        TcItemAttn a{};
+        a.q = ws.seg[i].qi; a.out = ws.att_b + off * kE; a.B = B; a.T = T; a.n_q = S; a.Sq_pad = Sp;
+        if (train) {
+          q.k_out = ws.seg[i].ki; q.vt_out = ws.seg[i].vti;
+          if (kv[i]) {
+            uint16_t* kvl = (uint16_t*)kv[i] + (size_t)l * B * T * Sp * 2 * kD;
+            q.k0_out = kvl;
+            q.vt0_out = kvl + (size_t)B * T * Sp * kD;
+          }
+          a.k = ws.seg[i].ki; a.vt = ws.seg[i].vti; a.n_kv = S; a.Skv_pad = Sp; a.shared_kv = 0;
+        } else {
+          const uint16_t* kvl = (const uint16_t*)kv[i] + (size_t)l * B * T * Np * 2 * kD;
+          a.k = kvl; a.vt = kvl + (size_t)B * T * Np * kD; a.n_kv = n_train; a.Skv_pad = Np; a.shared_kv = 1;
+        }
+        MMPFN_TRY(proj_gemm(q, st));
+        MMPFN_TRY(launch_tc_item_attn(a, st));
+        off += (long long)B * S * T;
+      }
+      MMPFN_TRY(out_proj_ln(lw, state, state_b, M, MMPFN_BF16, flat, st));
+    }
+    MMPFN_TRY(mlp(lw, state, state_b, M, MMPFN_BF16, flat, st));
+  }
+  return MMPFN_OK;
+}
+
+int mmpfn_layers_train_multi(const mmpfn_geometry* g, const mmpfn_weights* w, float* state_f32, uint16_t* state_bf16,
+                             const mmpfn_segment* segs, int n_seg, int S, void* const* kv, void* workspace,
+                             size_t workspace_bytes, void* stream) {
+  return layers_multi(g, w, state_f32, state_bf16, segs, n_seg, S, 0, 1, kv, workspace, workspace_bytes, (cudaStream_t)stream);
+}
+
+int mmpfn_layers_test_multi(const mmpfn_geometry* g, const mmpfn_weights* w, float* state_f32, uint16_t* state_bf16,
+                            const mmpfn_segment* segs, int n_seg, int S, int n_train, void* const* kv, void* workspace,
+                            size_t workspace_bytes, void* stream) {
+  return layers_multi(g, w, state_f32, state_bf16, segs, n_seg, S, n_train, 0, kv, workspace, workspace_bytes, (cudaStream_t)stream);
+}
+
 int mmpfn_decode(const mmpfn_geometry* g, const mmpfn_weights* w, const float* state, int B, int S, int T,
                  float* hidden_scratch, float* logits, void* stream) {
   MMPFN_TRY(check_geometry(g));

@@ -93,6 +93,8 @@ class B200InferenceEngine:
         self.nan_flag = torch.zeros(1, dtype=torch.int32, device=dev)
         self._graphs = {}
         self._pinned_bufs = {}
+        import os
+        self.multi_group = os.environ.get("MMPFN_MULTI_GROUP", "1") != "0"     # 0: one pass per group (A/B timing)
         self._stage_event = None
         self.launches_per_call = None
         if cache_context:
@@ -155,7 +157,31 @@ class B200InferenceEngine:
         img_test_dev = staged["img_test"]
         flag = self.nan_flag
         flag.zero_()
-        if self.cache_context:
+        # several groups with tables, bf16: one batched pass over all of them (flat sublayers launch once)
+        multi = (len(self.groups) > 1 and getattr(m, "precision", None) == _lib.BF16 and hasattr(m, "fit_contexts")
+                 and all(g["F"] >= 0 for g in self.groups) and self.multi_group)
+        if self.cache_context and multi:
+            tok_test = m.stem_image(img_test_dev) if img_test_dev is not None else None
+            lgs = m.predict_with_contexts([g["ctx"] for g in self.groups], staged["X_test"], img_tok_test=tok_test,
+                                          nan_flag=flag)
+            for g, lg in zip(self.groups, lgs):
+                for k, i in enumerate(g["idx"]):
+                    out[i] = lg[k]
+        elif multi:
+            tok = None
+            if img_test_dev is not None:
+                tok = m.stem_image(torch.cat([self.img_train_dev, img_test_dev], dim=0))
+            n_tr = self.groups[0]["y_train"].shape[1]
+            specs = [dict(X_train=g["X_train"], y_train=g["y_train"], X_all=torch.cat([g["X_train"], Xte], dim=1),
+                          img_tok_train=None if tok is None else tok[:n_tr], label_stats=g["label_stats"])
+                     for g, Xte in zip(self.groups, staged["X_test"])]
+            ctxs = m.fit_contexts(specs, nan_flag=flag)
+            lgs = m.predict_with_contexts(ctxs, staged["X_test"], img_tok_test=None if tok is None else tok[n_tr:],
+                                          nan_flag=flag)
+            for g, lg in zip(self.groups, lgs):
+                for k, i in enumerate(g["idx"]):
+                    out[i] = lg[k]
+        elif self.cache_context:
             tok_test = m.stem_image(img_test_dev) if img_test_dev is not None else None
             for g, Xte in zip(self.groups, staged["X_test"]):
                 lg = m.predict_with_context(g["ctx"], Xte, None, img_tok_test=tok_test, check=False, nan_flag=flag)

@@ -174,7 +174,7 @@ class B200PerFeatureTransformer:
             mask[b] = torch.unique(bits[b]).sum()
         return y_train.to(torch.float32).mean(dim=1).contiguous(), mask
 
-    def embed(self, X, stats, img_tok, y, y_mean, y_mask, pos_emb, *, B, S, F, x_bstride, y_bstride, nan_flag):
+    def embed(self, X, stats, img_tok, y, y_mean, y_mask, pos_emb, *, B, S, F, x_bstride, y_bstride, nan_flag, out=None):
         """Token assembly -> (state_f32 [B,S,T,E], state_bf16 or None)."""
         G = self._n_groups(F) if X is not None else 0
         # img_tok [S, H, E]: shared by the B entries; [B, S, H, E]: one set per entry (packed tasks)
@@ -187,9 +187,13 @@ class B200PerFeatureTransformer:
             img_bstride = img_tok.shape[1] * img_tok.shape[2] * img_tok.shape[3]
         T = G + H_img + 1
         E = self.geom.emsize
-        state = torch.empty((B, S, T, E), dtype=torch.float32, device=self.device)
-        state_b = torch.empty((B, S, T, E), dtype=torch.bfloat16, device=self.device) \
-            if self.precision == _lib.BF16 else None
+        if out is not None:          # views into a buffer shared by several estimator groups (layers_*_multi)
+            state, state_b = out
+            assert tuple(state.shape) == (B, S, T, E) and state.is_contiguous()
+        else:
+            state = torch.empty((B, S, T, E), dtype=torch.float32, device=self.device)
+            state_b = torch.empty((B, S, T, E), dtype=torch.bfloat16, device=self.device) \
+                if self.precision == _lib.BF16 else None
         _lib.check(self.lib.mmpfn_stem_tokens(
             self._g, self._w, _ptr(X), _ptr(stats), _ptr(img_tok), y.data_ptr(), y_mean.data_ptr(),
             y_mask.data_ptr(), pos_emb.data_ptr(), B, S, F if X is not None else 0, H_img, x_bstride, y_bstride,
@@ -212,6 +216,23 @@ class B200PerFeatureTransformer:
         _lib.check(self.lib.mmpfn_layers_test(self._g, self._w, state.data_ptr(), _ptr(state_b), B, S, T, n_train,
                                               self.precision, kv.data_ptr(), ws.data_ptr(), nbytes, self._stream()),
                    "mmpfn_layers_test")
+
+    def _layers_multi(self, state, state_b, segs, S: int, kvs, n_train: Optional[int]):
+        """``state`` / ``state_b``: flat [M_total, E] buffers holding the segments' [B_i, S, T_i, E] states back
+        to back; ``segs``: [(B_i, T_i)]; ``kvs``: one context tensor per segment."""
+        n = len(segs)
+        arr = (_lib.Segment * n)(*[_lib.Segment(int(b), int(t)) for b, t in segs])
+        kvp = (C.c_void_p * n)(*[kv.data_ptr() for kv in kvs])
+        nbytes = self.lib.mmpfn_layers_multi_ws_bytes(self._g, arr, n, S)
+        ws = self._scratch("layers", nbytes)
+        if n_train is None:
+            _lib.check(self.lib.mmpfn_layers_train_multi(self._g, self._w, state.data_ptr(), state_b.data_ptr(), arr, n, S,
+                                                         kvp, ws.data_ptr(), nbytes, self._stream()),
+                       "mmpfn_layers_train_multi")
+        else:
+            _lib.check(self.lib.mmpfn_layers_test_multi(self._g, self._w, state.data_ptr(), state_b.data_ptr(), arr, n, S,
+                                                        n_train, kvp, ws.data_ptr(), nbytes, self._stream()),
+                       "mmpfn_layers_test_multi")
 
     def alloc_kv(self, B: int, n_train: int, T: int) -> torch.Tensor:
         nbytes = self.lib.mmpfn_kv_bytes(self._g, B, n_train, T, self.precision)
@@ -332,6 +353,72 @@ class B200PerFeatureTransformer:
             if check:
                 self._check_nan(flag)
             return logits
+
+    # ---- several estimator groups at once (bf16): one launch per flat sublayer for all of them ----------
+    def _group_buffers(self, shapes):
+        """One fp32 + one bf16 buffer for states of the given [(B, S, T)] shapes, and the per-group views."""
+        E = self.geom.emsize
+        total = sum(b * s * t for b, s, t in shapes)
+        st = torch.empty((total, E), dtype=torch.float32, device=self.device)
+        stb = torch.empty((total, E), dtype=torch.bfloat16, device=self.device)
+        views, off = [], 0
+        for b, s, t in shapes:
+            n = b * s * t
+            views.append((st[off:off + n].view(b, s, t, E), stb[off:off + n].view(b, s, t, E)))
+            off += n
+        return st, stb, views
+
+    def fit_contexts(self, specs, *, nan_flag=None):
+        """``fit_context`` for several estimator groups that share the train rows (same n_train) — specs:
+        dicts with ``X_train [B, Ntr, F]``, ``y_train [B, Ntr]``, optional ``X_all``, ``img_tok_train``,
+        ``label_stats``.  Same results as one ``fit_context`` per group; the layers run as
+        ``mmpfn_layers_train_multi``."""
+        assert self.precision == _lib.BF16
+        with torch.cuda.device(self.device):
+            flag = nan_flag if nan_flag is not None else torch.zeros(1, dtype=torch.int32, device=self.device)
+            prep = []
+            for sp in specs:
+                X_train, _ = self._prep(sp["X_train"], None)
+                y_train = sp["y_train"].to(self.device, torch.float32).contiguous()
+                B, n_train = y_train.shape
+                F = X_train.shape[2]
+                X_all = sp.get("X_all")
+                if X_all is not None:
+                    X_all, _ = self._prep(X_all, None)
+                stats = self.stem_tab_fit(X_all if X_all is not None else X_train, n_train)
+                tok = sp.get("img_tok_train")
+                y_mean, y_mask = sp["label_stats"] if sp.get("label_stats") is not None else self.label_stats(y_train)
+                T = self._n_groups(F) + (0 if tok is None else tok.shape[-2]) + 1
+                prep.append(dict(X=X_train, y=y_train, B=B, n_train=n_train, F=F, stats=stats, tok=tok, y_mean=y_mean,
+                                 y_mask=y_mask, T=T, pos=self.positional_embeddings(T - 1)))
+            n_train = prep[0]["n_train"]
+            assert all(p["n_train"] == n_train for p in prep)
+            st, stb, views = self._group_buffers([(p["B"], n_train, p["T"]) for p in prep])
+            for p, v in zip(prep, views):
+                self.embed(p["X"], p["stats"], p["tok"], p["y"], p["y_mean"], p["y_mask"], p["pos"], B=p["B"], S=n_train,
+                           F=p["F"], x_bstride=n_train * p["F"], y_bstride=n_train, nan_flag=flag, out=v)
+            kvs = [self.alloc_kv(p["B"], n_train, p["T"]) for p in prep]
+            self._layers_multi(st, stb, [(p["B"], p["T"]) for p in prep], n_train, kvs, None)
+            return [TrainContext(B=p["B"], n_train=n_train, F=p["F"], T=p["T"], n_tok=0, kv=kv, tab_stats=p["stats"],
+                                 y_mean=p["y_mean"], y_mask=p["y_mask"], pos_emb=p["pos"], precision=self.precision)
+                    for p, kv in zip(prep, kvs)]
+
+    def predict_with_contexts(self, ctxs, X_tests, *, img_tok_test=None, nan_flag=None):
+        """``predict_with_context`` for several groups at once (same test rows) -> [logits [B_i, Nte, n_out]]."""
+        assert self.precision == _lib.BF16
+        with torch.cuda.device(self.device):
+            flag = nan_flag if nan_flag is not None else torch.zeros(1, dtype=torch.int32, device=self.device)
+            Xs = [self._prep(X, None)[0] for X in X_tests]
+            n_test = Xs[0].shape[1]
+            y_nan = torch.full((1, n_test), float("nan"), dtype=torch.float32, device=self.device)
+            st, stb, views = self._group_buffers([(c.B, n_test, c.T) for c in ctxs])
+            for c, X, v in zip(ctxs, Xs, views):
+                if X.shape[0] != c.B or X.shape[2] != c.F or X.shape[1] != n_test:
+                    raise ValueError("test tables do not match their contexts")
+                self.embed(X, c.tab_stats, img_tok_test, y_nan, c.y_mean, c.y_mask, c.pos_emb, B=c.B, S=n_test, F=c.F,
+                           x_bstride=n_test * c.F, y_bstride=0, nan_flag=flag, out=v)
+            self._layers_multi(st, stb, [(c.B, c.T) for c in ctxs], n_test, [c.kv for c in ctxs], ctxs[0].n_train)
+            return [self.decode(v[0]) for v in views]
 
     def forward_batch(self, X_full, img_full, y_train, *, check=True):
         """Reference-equivalent joint forward for B estimators sharing the image embeddings:

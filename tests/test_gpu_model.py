@@ -183,3 +183,27 @@ def test_model_random_configs_vs_oracle(seed):
         logits = _run_joint(model, X, img, y)
         p, pr = softmax_np(logits[:, :n_cls] / 0.9), softmax_np(ref[:, :n_cls] / 0.9)
         assert np.abs(p - pr).max() <= P_TOL[precision], (precision, mixer, mgm, cap, n_tr, n_te, F, n_tok, n_cls)
+
+
+@pytest.mark.parametrize("fit_mode", ["fit_preprocessors", "fit_with_cache"])
+def test_multi_group_pass_equals_per_group(fit_mode):
+    """Estimator groups of different token counts through mmpfn_layers_*_multi (flat sublayers launched once
+    for all groups) vs one pass per group: identical logits, bit for bit."""
+    from multimodalpfn_b200.classifier import MMPFNClassifier
+    from multimodalpfn_b200.preprocessing import transform_all
+    from multimodalpfn_b200.synth import Geometry, make_dataset, make_state_dict
+    geom = Geometry(mgm_heads=2, cap_heads=4)
+    sd = make_state_dict(geom, seed=3)
+    d = make_dataset("pad_ufes_small", 0)
+    clf = MMPFNClassifier(mixer_type="MGM+CAP", mgm_heads=2, cap_heads=4, features_per_group=2, n_estimators=4,
+                          model_path=(sd, geom), device="cuda", inference_precision="bf16",
+                          ignore_pretraining_limits=True, random_state=0, fit_mode=fit_mode)
+    clf.fit(d["X_train"], d["img_train"], d["y_train"])
+    eng = clf.executor_
+    assert len(eng.groups) == 2
+    staged = eng.stage(transform_all(clf.members_, d["X_test"]), d["img_test"])
+    eng.multi_group = True
+    a = eng.logits_staged(staged).clone()
+    eng.multi_group = False
+    b = eng.logits_staged(staged).clone()
+    assert torch.isfinite(a).all() and torch.equal(a, b)
