@@ -94,23 +94,32 @@ class ShardedEngine:
             n_img_train = eng.img_train_dev.shape[0]
             tok = m.stem_image(torch.cat([eng.img_train_dev, img_test_dev], dim=0))
         out = [None] * len(self.members)
-        # 1. build the contexts this rank owns
+        # 1. build the contexts this rank owns (several sub-batches of different token counts: one batched
+        #    pass, model.fit_contexts, when the model offers it)
         mine: Dict[int, TrainContext] = {}
-        for si, sub in enumerate(self.subs):
-            if sub.owner != self.rank:
-                continue
+        owned = [(si, sub) for si, sub in enumerate(self.subs) if sub.owner == self.rank]
+        specs = []
+        for si, sub in owned:
             g = eng.groups[sub.group]
             Xtr = None if g["X_train"] is None else g["X_train"][sub.pos].contiguous()
             Xte = staged["X_test"][sub.group]
             Xte = None if Xte is None else Xte[sub.pos].contiguous()
             ytr = g["y_train"][sub.pos].contiguous()
             n_tr = ytr.shape[1]
-            X_full = None if Xte is None else torch.cat([Xtr, Xte], dim=1)
             ls = g["label_stats"]
-            mine[si] = m.fit_context(Xtr, None, ytr, X_all=X_full,
-                                     img_tok_train=None if tok is None else tok[:n_tr], check=False,
-                                     label_stats=(ls[0][sub.pos].contiguous(), ls[1][sub.pos].contiguous()),
-                                     nan_flag=eng.nan_flag)
+            specs.append(dict(X_train=Xtr, y_train=ytr, X_all=None if Xte is None else torch.cat([Xtr, Xte], dim=1),
+                              img_tok_train=None if tok is None else tok[:n_tr],
+                              label_stats=(ls[0][sub.pos].contiguous(), ls[1][sub.pos].contiguous())))
+        multi = (getattr(eng, "multi_group", False) and hasattr(m, "fit_contexts") and m.precision == 1
+                 and all(sp["X_train"] is not None for sp in specs))
+        if multi and len(specs) > 1:
+            for (si, _), c in zip(owned, m.fit_contexts(specs, nan_flag=eng.nan_flag)):
+                mine[si] = c
+        else:
+            for (si, _), sp in zip(owned, specs):
+                mine[si] = m.fit_context(sp["X_train"], None, sp["y_train"], X_all=sp["X_all"],
+                                         img_tok_train=sp["img_tok_train"], check=False,
+                                         label_stats=sp["label_stats"], nan_flag=eng.nan_flag)
         # 2. replicate every context (the exchange step)
         ctxs: Dict[int, TrainContext] = {}
         for si, sub in enumerate(self.subs):
@@ -137,6 +146,7 @@ class ShardedEngine:
         #    test pass launches once per group (B = 4 here) instead of once per owner (B = 1 at W = 8:
         #    8 x as many launches of kernels that are already latency bound at 300 rows).
         tok_test = None if tok is None else tok[n_img_train:]
+        merged = []
         for gi, g in enumerate(eng.groups):
             subs = [(si, sub) for si, sub in enumerate(self.subs) if sub.group == gi]
             if len(subs) == 1:
@@ -157,8 +167,13 @@ class ShardedEngine:
                 kv = m.merge_kv([(ctxs[si].kv, sub.pos) for si, sub in subs], Bg, c0.n_train, c0.T)
                 ctx = TrainContext(B=Bg, n_train=c0.n_train, F=c0.F, T=c0.T, n_tok=0, kv=kv, tab_stats=stats,
                                    y_mean=y_mean, y_mask=y_mask, pos_emb=c0.pos_emb, precision=m.precision)
-            lg = m.predict_with_context(ctx, staged["X_test"][gi], None, img_tok_test=tok_test, check=False,
-                                        nan_flag=eng.nan_flag)
+            merged.append(ctx)
+        if multi and len(merged) > 1:
+            lgs = m.predict_with_contexts(merged, staged["X_test"], img_tok_test=tok_test, nan_flag=eng.nan_flag)
+        else:
+            lgs = [m.predict_with_context(ctx, staged["X_test"][gi], None, img_tok_test=tok_test, check=False,
+                                          nan_flag=eng.nan_flag) for gi, ctx in enumerate(merged)]
+        for g, lg in zip(eng.groups, lgs):
             for k, i in enumerate(g["idx"]):
                 out[i] = lg[k]
         return torch.stack(out)
