@@ -224,7 +224,10 @@ int mmpfn_mlp_bf16(float* state_f32, uint16_t* state_bf16, const uint16_t* w1, c
 /* Item-axis attention alone (layer.py:341-379), bf16 tcgen05 kernel, for unit tests and roofline timing.
  *   q  [B*T*nhead][Sq_pad][32]   k [planes_kv][Skv_pad][32]   vt [planes_kv][32][Skv_pad]   (bf16)
  *   planes_kv = B*T (shared_kv = 1: every query head reads head 0) or B*T*nhead (shared_kv = 0)
- *   out [B][n_q][T][nhead*32] bf16.  Sq_pad/Skv_pad are the allocated row counts (multiples of 8). */
+ *   out [B][n_q][T][nhead*32] bf16.  Sq_pad/Skv_pad are the allocated row counts (multiples of 8).
+ * With shared_kv = 1 the six query heads of a column may be stacked on the tile row axis (fewer, fuller
+ * tiles): the rows n_q .. Sq_pad-1 of every q plane are then read (their results are dropped) and should
+ * hold finite values — mmpfn_item_qkv_bf16 writes zeros there. */
 int mmpfn_item_attention_bf16(const uint16_t* q, const uint16_t* k, const uint16_t* vt, int B, int T, int n_q,
                               int Sq_pad, int n_kv, int Skv_pad, int shared_kv, uint16_t* out, void* stream);
 
