@@ -158,7 +158,7 @@ class B200InferenceEngine:
         flag = self.nan_flag
         flag.zero_()
         # several groups with tables, bf16: one batched pass over all of them (flat sublayers launch once)
-        multi = (len(self.groups) > 1 and getattr(m, "precision", None) == _lib.BF16 and hasattr(m, "fit_contexts")
+        multi = (1 < len(self.groups) <= 8 and getattr(m, "precision", None) == _lib.BF16 and hasattr(m, "fit_contexts")
                  and all(g["F"] >= 0 for g in self.groups) and self.multi_group)
         if self.cache_context and multi:
             tok_test = m.stem_image(img_test_dev) if img_test_dev is not None else None
