@@ -43,6 +43,11 @@ def test_no_cpu_fallback():
     rc = lib.mmpfn_layernorm(None, None, None, None, 1, 192, None, None, None)
     assert rc == -2  # MMPFN_ENODEVICE
     assert b"no CPU fallback" in lib.mmpfn_last_error()
+    g = _lib.Geometry(192, 6, 768, 12, 10, 2, 768, 8, 8, 2)
+    segs = (_lib.Segment * 1)(_lib.Segment(1, 5))
+    kv = (ctypes.c_void_p * 1)(None)
+    assert lib.mmpfn_layers_train_multi(ctypes.byref(g), None, None, None, segs, 1, 10, kv, None, 0, None) == -2
+    assert lib.mmpfn_item_qkv_bf16(None, None, 1, 1, 2, 64, 3, None, None, None, None, None, None) == -2
     from multimodalpfn_b200.model import B200PerFeatureTransformer
     from multimodalpfn_b200.synth import Geometry
     with pytest.raises(RuntimeError):
@@ -58,3 +63,8 @@ def test_sizes_need_no_device():
     assert lib.mmpfn_layers_ws_bytes(ctypes.byref(g), 1, 100, 20, 0) > 0
     assert lib.mmpfn_kv_bytes(ctypes.byref(g), 2, 100, 20, 0) == 12 * 2 * 20 * 100 * 64 * 4
     assert lib.mmpfn_kv_bytes(ctypes.byref(g), 2, 100, 20, 1) == 12 * 2 * 20 * 128 * 64 * 2
+    segs = (_lib.Segment * 2)(_lib.Segment(4, 27), _lib.Segment(4, 20))
+    M = 4 * 100 * 27 + 4 * 100 * 20
+    planes = 3 * 4 * (27 + 20) * 6 * 128 * 32 * 2
+    assert lib.mmpfn_layers_multi_ws_bytes(ctypes.byref(g), segs, 2, 100) >= M * 768 * 2 + M * 192 * 2 + planes
+    assert lib.mmpfn_layers_multi_ws_bytes(ctypes.byref(g), segs, 9, 100) == 0        # more than MMPFN_MAX_SEGMENTS
