@@ -112,7 +112,7 @@ class ShardedEngine:
                               label_stats=(ls[0][sub.pos].contiguous(), ls[1][sub.pos].contiguous())))
         multi = (getattr(eng, "multi_group", False) and hasattr(m, "fit_contexts") and m.precision == 1
                  and len(specs) <= 8 and len(eng.groups) <= 8      # MMPFN_MAX_SEGMENTS
-                 and all(sp["X_train"] is not None for sp in specs))
+                 and all(sp["X_train"] is not None for sp in specs) and all(g["F"] >= 0 for g in eng.groups))
         if multi and len(specs) > 1:
             for (si, _), c in zip(owned, m.fit_contexts(specs, nan_flag=eng.nan_flag)):
                 mine[si] = c
