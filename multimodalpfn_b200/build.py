@@ -14,14 +14,17 @@ import subprocess
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 INCLUDE = os.path.join(os.path.dirname(HERE), "include")
-LIB = os.path.join(HERE, "libmmpfn_b200.so")
-STAMP = os.path.join(HERE, ".libmmpfn_b200.stamp")
+# MMPFN_DEBUG_LIB=1 selects the tuning build (-DMMPFN_DEBUG: kernel-variant switches read from the
+# environment, used by tools/ only); the product library has none of them.
+DEBUG = os.environ.get("MMPFN_DEBUG_LIB", "0") == "1"
+LIB = os.path.join(HERE, "libmmpfn_b200_dbg.so" if DEBUG else "libmmpfn_b200.so")
+STAMP = os.path.join(HERE, ".libmmpfn_b200_dbg.stamp" if DEBUG else ".libmmpfn_b200.stamp")
 SOURCES = ["api.cu", "kernels_f32.cu", "kernels_stem.cu", "kernels_tc.cu", "kernels_attn.cu", "kernels_mlp.cu", "kernels_rowgemm.cu"]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
     "--expt-relaxed-constexpr", "-Xcompiler", "-fPIC", "-shared", "-cudart", "static",
     "-Xptxas", "-v",
-]
+] + (["-DMMPFN_DEBUG"] if DEBUG else [])
 
 
 def _nvcc() -> str:
@@ -56,7 +59,7 @@ def build(force: bool = False, verbose: bool = False) -> str:
     res = subprocess.run(cmd, capture_output=True, text=True)
     if res.returncode != 0:
         raise RuntimeError("nvcc failed:\n" + res.stdout + res.stderr)
-    with open(os.path.join(HERE, "build_ptxas.log"), "w") as f:
+    with open(os.path.join(HERE, "build_ptxas_dbg.log" if DEBUG else "build_ptxas.log"), "w") as f:
         f.write(res.stdout + res.stderr)
     if verbose:
         print(res.stdout + res.stderr)

@@ -23,7 +23,9 @@ int check_geometry(const mmpfn_geometry* g);
 
 inline int count_launch() {
   g_launches.fetch_add(1, std::memory_order_relaxed);
-  cudaError_t e = cudaPeekAtLastError();
+  // cudaGetLastError, not Peek: the library links cudart statically and owns this per-thread error
+  // state; a non-sticky launch failure must be reported once and cleared, not poison every later call
+  cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) {
     set_error("kernel launch failed: %s", cudaGetErrorString(e));
     return MMPFN_ECUDA;

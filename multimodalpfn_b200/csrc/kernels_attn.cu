@@ -3,23 +3,26 @@
 //
 //   S = Q K^T and O += P V on tcgen05 (accumulators in TMEM, operands staged by TMA), online softmax
 //   in fp32 by four warps (thread = query row).  P goes back into tensor memory over the S columns it
-//   came from (bf16 pairs) and the second MMA reads its A operand there (PT = true, the default); the
-//   older hand-off through a 128B-swizzled shared-memory tile is kept as PT = false for A/B timing.
+//   came from (bf16 pairs) and the second MMA reads its A operand there: no st.shared, no proxy fence.
 //
-// At d = 32 every exponential buys only 128 tensor FLOP, so the kernel lives on the MUFU/FMA pipes
-// (16 ex2/clk/SM = 595 TFLOP/s at 1965 MHz), not on the tensor pipe: everything here is arranged so
-// that the softmax warps never wait (S double buffered in TMEM, no row maximum in the inner loop,
-// per-parity barriers) and that enough of them are resident to keep the MUFU queue full.
+// At d = 32 every exponential buys only 128 tensor FLOP, so the kernel lives on the MUFU pipe
+// (16 ex2/clk/SM = 595 TFLOP/s at 1965 MHz if every exponential went there) and on the issue slots of
+// the four schedulers, not on the tensor pipe.  Round-1 profile (profiles/r01_ncu_stalls_v6_*): the
+// TMA and MMA role warps executed 117 and 164 instructions per key tile (bounded two-barrier polls,
+// descriptor arithmetic, four commits) on schedulers 0 and 1, next to a softmax warp that needs ~230 of
+// the 336 MUFU-bound cycles of a tile: scheduler 1 was ISSUE bound and, the four softmax warps of a CTA
+// moving in lockstep, held the MUFU pipe of all four at 76 %.  This version
+//   * hands every per-tile event to ONE barrier per S buffer: the MMA thread commits once per tile
+//     (done[s]: "P V(j) and S(j+2) have completed") and the TMA thread refills V(j+2) and K(j+4) on one
+//     barrier (kv_full[s]) behind it — 1 wait + 1 expect_tx + 2 loads, and 2 waits + 5 MMAs + 1 commit;
+//   * takes PP of every 24 key PAIRS through a packed (FFMA2/FADD2) degree-3 polynomial 2^x on the FMA
+//     pipe — 5 issue slots per exponential instead of 9 for the scalar form — with the exponent splice
+//     clamped by one VIADDMNMX.RELU instead of two FMNMX.
 //
-// Two tile shapes (template BK = keys per tile):
-//   BK = 48,  4 CTAs/SM   TMEM: S0 [0,48)  S1 [48,96)   O [96,128)   — the default: four softmax warps
-//                         per scheduler (460 TFLOP/s at the cfg2 train shape)
-//   BK = 112, 2 CTAs/SM   TMEM: S0 [0,112) S1 [112,224) O [224,256)  — MMPFN_ATTN_BK=112 (411 TFLOP/s)
-//
+// Tile: BK = 48 keys, 4 CTAs/SM.  TMEM: S0 [0,48)  S1 [48,96)  O [96,128).
 // Test pass (every query head of a column reads that column's head-0 K/V): the six heads are stacked on
 // the tile's row axis, so 6 x 300 query rows fill 15 tiles of 128 instead of 18.
-//
-// Every mbarrier wait is bounded (trap after ~2 s) so that a protocol bug cannot hang the GPU.
+// Every mbarrier wait is bounded (trap) so that a protocol bug cannot hang the GPU.
 #include "tc_common.cuh"
 
 namespace mmpfn {
@@ -28,24 +31,22 @@ namespace {
 constexpr int A_BQ = 128;
 constexpr int A_Q_BYTES = A_BQ * kD * 2;          // 8 KB  (64B rows, 64B swizzle)
 constexpr int A_THREADS = 192;
-constexpr int kAttnPolyDefault = 4;
+constexpr int kPolyPairsDefault = 6;              // of 24 pairs per tile (measured optimum)
 
-template <int BK, bool PT = false>
+template <int BK>
 struct AttnCfg {
-  static constexpr int kNKB = (BK + 63) / 64;                 // 64-key k-blocks of the P and V^T tiles
+  static constexpr int kNKB = (BK + 63) / 64;                 // 64-key k-blocks of the V^T tile
   static constexpr int kKTx = BK * kD * 2;                    // bytes of one K tile (64 B per key)
-  static constexpr int kKSlot = BK > 64 ? 8192 : kKTx;          // slot stride: a multiple of 512 (the 64B-swizzle atom)
+  static constexpr int kKSlot = (kKTx + 511) / 512 * 512;     // slot stride: a multiple of the 64B-swizzle atom
   static constexpr int kVtBytes = kNKB * kD * 128;            // [32 d][64 keys = 128 B] per k-block, 128B swizzle
-  static constexpr int kPBytes = PT ? 0 : kNKB * A_BQ * 128;  // [128 rows][128 B] per k-block, 128B swizzle (P in TMEM: none)
   static constexpr int kOffK = A_Q_BYTES;
-  static constexpr int kOffVt = kOffK + 2 * kKSlot;
-  static constexpr int kOffP = (kOffVt + 2 * kVtBytes + 1023) / 1024 * 1024;
-  static constexpr int kOffBar = kOffP + 2 * kPBytes;
-  static constexpr int kSmem = kOffBar + 256 + 1024;
+  static constexpr int kOffVt = (kOffK + 2 * kKSlot + 1023) / 1024 * 1024;
+  static constexpr int kOffBar = kOffVt + 2 * kVtBytes;
+  static constexpr int kSmem = kOffBar + 128 + 1024;
   static constexpr int kTmemCols = 2 * BK + kD <= 128 ? 128 : 256;
   static constexpr int kMinCtas = 512 / kTmemCols;
   static_assert(2 * BK + kD <= 256, "two S accumulators and O must fit the CTA's TMEM share");
-  static_assert(BK % 16 == 0 && kKSlot % 512 == 0, "tile shape");
+  static_assert(BK % 16 == 0, "tile shape");
 };
 
 struct AttnArgs {
@@ -54,13 +55,90 @@ struct AttnArgs {
   int stack_rows;   // > 0: the six query heads of a (b, t) column are stacked on the tile's row axis, Sq_pad rows each
 };
 
-// DBG != 0: knock-out timing experiments (results are wrong): 1 no exp, 2 no S load from TMEM,
-// 4 no P store, 8 no P V MMA, 16 no S MMA, 32 no row maximum; 64 = clock64 trace of one CTA.
-__device__ long long g_attn_trace[4096];
-#define ATTN_TRACE(slot)                                                          \
-  do {                                                                            \
-    if ((DBG & 64) && blockIdx.x == 5001) g_attn_trace[(slot)] = clock64();       \
+#ifdef MMPFN_DEBUG
+// tuning build only: clock64 stamps of one CTA (tools/attn_trace.py)
+__device__ long long g_attn_trace[8192];
+#define ATTN_TRACE(slot)                                                      \
+  do {                                                                        \
+    if (blockIdx.x == 5001 && (slot) < 8192) g_attn_trace[(slot)] = clock64(); \
   } while (0)
+#else
+#define ATTN_TRACE(slot) do {} while (0)
+#endif
+
+// A poll of three instructions per probe (try_wait parks the thread in hardware until the barrier moves
+// or the hint expires); a wait that outlives ~2^20 probes traps instead of hanging the GPU.
+__device__ __forceinline__ void mbar_wait_lean(uint32_t addr, uint32_t parity) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t.reg .u32 n;\n\t"
+      "mov.u32 n, 0;\n\t"
+      "WAIT_%=:\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1, %2;\n\t"
+      "@p bra DONE_%=;\n\t"
+      "add.u32 n, n, 1;\n\t"
+      "setp.lt.u32 p, n, 1048576;\n\t"
+      "@p bra WAIT_%=;\n\t"
+      "trap;\n\t"
+      "DONE_%=:\n\t}"
+      ::"r"(addr), "r"(parity), "r"(20000u)
+      : "memory");
+}
+__device__ __forceinline__ bool mbar_test_addr(uint32_t addr, uint32_t parity) {
+  uint32_t done;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(done)
+      : "r"(addr), "r"(parity)
+      : "memory");
+  return done != 0;
+}
+__device__ __forceinline__ void mbar_expect_tx_addr(uint32_t addr, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(addr), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void umma_commit_addr(uint32_t addr) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(addr) : "memory");
+}
+__device__ __forceinline__ void tma_load_3d_addr(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1, int c2) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+      ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1), "r"(c2)
+      : "memory");
+}
+__device__ __forceinline__ uint64_t sub_f32x2(uint64_t a, uint64_t b) {
+  uint64_t r;
+  asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+  return r;
+}
+
+// 2^x for a PAIR of scores on the FMA / ALU pipes (no MUFU), ten instructions:
+//   r = x + 1.5*2^23 (round(x) lands in the low mantissa bits), f = x - (r - 1.5*2^23) in [-0.5, 0.5]   3 FADD2
+//   2^f * 2^-100 by a degree-3 minimax polynomial (max relative error 7.6e-5 << bf16 rounding of P)        3 FFMA2
+//   t = clamp(round(x) + 100, 0, 226) by one VIADDMNMX.RELU each; result bits = poly bits + (t << 23)       2 + 2 LEA
+// i.e. 2^x for x in [-100, 126]; below, the result saturates at ~2^-100 (nothing: the row reference is at
+// most 2^8 above), above at ~2^126 (the row sum overflows the limit and the tile is repeated against the
+// true maximum — never a wrapped exponent).  NaN / +inf in give NaN out, which fails the row-sum test too.
+constexpr float kPolyScale = 7.888609052210118e-31f;     // 2^-100
+__device__ __forceinline__ void poly_exp2_pair(uint32_t& a, uint32_t& b) {
+  const uint64_t x2 = pack_f32x2(__uint_as_float(a), __uint_as_float(b));
+  const uint64_t m2 = pack_f32x2(12582912.0f, 12582912.0f);
+  const uint64_t r2 = add_f32x2(x2, m2);
+  const uint64_t f2 = sub_f32x2(x2, sub_f32x2(r2, m2));
+  uint64_t p2 = fma_f32x2(pack_f32x2(0.05520550534129143f * kPolyScale, 0.05520550534129143f * kPolyScale), f2,
+                          pack_f32x2(0.24261397123336792f * kPolyScale, 0.24261397123336792f * kPolyScale));
+  p2 = fma_f32x2(p2, f2, pack_f32x2(0.6932547688484192f * kPolyScale, 0.6932547688484192f * kPolyScale));
+  p2 = fma_f32x2(p2, f2, pack_f32x2(0.9999276995658875f * kPolyScale, 0.9999276995658875f * kPolyScale));
+  float pl, ph, rl, rh;
+  unpack_f32x2(p2, pl, ph);
+  unpack_f32x2(r2, rl, rh);
+  const int tl = __viaddmin_s32_relu(__float_as_int(rl), 100 - 0x4B400000, 226);
+  const int th = __viaddmin_s32_relu(__float_as_int(rh), 100 - 0x4B400000, 226);
+  a = (uint32_t)(tl * 0x800000 + __float_as_int(pl));
+  b = (uint32_t)(th * 0x800000 + __float_as_int(ph));
+}
+// which of the NP key pairs of a tile take the polynomial: PP of NP, evenly spread
+__host__ __device__ constexpr bool poly_pair(int k, int PP, int NP) { return ((k + 1) * PP) / NP != (k * PP) / NP; }
 
 // n consecutive fp32 columns of this warp's 32 TMEM lanes into v[0..n)
 template <int N>
@@ -118,37 +196,29 @@ __device__ __forceinline__ void tmem_st_cols(uint32_t taddr, const uint32_t* v) 
   }
 }
 
+// Barriers (phase n of each counts from 0):
+//   q_full        Q, K(0), K(1) have landed
+//   kv_full[s]    n-th refill of slot s: V^T(2n+s) and K(2n+s+2) have landed
+//   p_full[s]     n-th time the four softmax warps have written P(2n+s) into TMEM buffer s
+//   done[s]       n = 0: S(s) of the prologue has completed; n >= 1: iteration j = 2(n-1)+s of the MMA
+//                 thread — P V(j), then S(j+2) into buffer s — has.  One arrival tells the softmax
+//                 that S(j+2) is in TMEM and that O holds P V(j), and the TMA thread that V slot s and
+//                 K slot s (K(j+2), just consumed) are free.
 //   warps 0-3  softmax, thread = query row (TMEM lane quarter = warp)
-//   warp 4     TMA producer (K and V^T on separate rings) + TMEM allocation
-//   warp 5     MMA issue: S = Q K^T into TMEM, O += P V with P read from shared memory
-// With S double buffered, S(j+2) is issued as soon as the softmax has pulled S(j) into registers, a
-// whole tile before it is needed: the mbarrier round trips (try_wait wake-up, tcgen05.commit arrival:
-// ~1900 cycles per tile measured with the math knocked out) leave the softmax path.
-// PT = true: P never touches shared memory.  The softmax writes it (bf16 pairs, 24 columns for 48 keys)
-// over the S columns it came from and the P V MMA reads its A operand from tensor memory: no st.shared,
-// no generic->async proxy fence (a full MEMBAR per thread and tile), and the S buffer of tile j simply
-// stays occupied until P V(j) has run — S(j+2) is issued right behind it by the same thread.
-template <int BK, int PN, int DBG, bool PT>
-__global__ void __launch_bounds__(A_THREADS, AttnCfg<BK, PT>::kMinCtas)
+//   warp 4     TMA producer + TMEM allocation
+//   warp 5     MMA issue
+template <int BK, int PP>
+__global__ void __launch_bounds__(A_THREADS, AttnCfg<BK>::kMinCtas)
     tc_item_attn_kernel(const __grid_constant__ CUtensorMap map_q, const __grid_constant__ CUtensorMap map_k,
                         const __grid_constant__ CUtensorMap map_vt, const AttnArgs p) {
-  using C = AttnCfg<BK, PT>;
+  using C = AttnCfg<BK>;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
   uint64_t* bars = (uint64_t*)(smem + C::kOffBar);
-  uint64_t* q_full = bars;
-  uint64_t* k_full = bars + 1;         // [2]  K slot of tile j is free once S(j) has been computed,
-  uint64_t* k_empty = bars + 3;        // [2]  V^T slot once P V(j) has
-  uint64_t* v_full = bars + 5;         // [2]
-  uint64_t* v_empty = bars + 7;        // [2]
-  uint64_t* s_full = bars + 9;         // [2]  S(j) is in TMEM buffer j & 1
-  uint64_t* s_free = bars + 11;        // [2]  ... and has been pulled into the softmax registers
-  uint64_t* p_full = bars + 13;        // [2]  P(j) is in shared memory buffer j & 1.  Per buffer: a warp may run one
-                                       //      tile ahead of the slowest one, and its arrival must not count for it
-  uint64_t* pv_done = bars + 15;       // [2]  P V(j) has completed -> pv_done[j & 1].  The softmax only looks at it when
-                                       //      it has to (rescale, final read); with one barrier per parity of j a
-                                       //      parity wait stays unambiguous although phases go unobserved
-  uint32_t* tmem_slot = (uint32_t*)(bars + 17);
+  const uint32_t sbase = smem_u32(smem);
+  const uint32_t bar0 = sbase + C::kOffBar;
+  const uint32_t q_full = bar0, kv_full = bar0 + 8, p_full = bar0 + 24, done = bar0 + 40;   // [2] each after q_full
+  uint32_t* tmem_slot = (uint32_t*)(bars + 8);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   // Train pass: plane = (b*T + t)*kH + h, q tiles of a plane are adjacent CTAs.  Test pass (all six query
@@ -165,16 +235,11 @@ __global__ void __launch_bounds__(A_THREADS, AttnCfg<BK, PT>::kMinCtas)
     prefetch_tmap(&map_q);
     prefetch_tmap(&map_k);
     prefetch_tmap(&map_vt);
-    mbar_init(q_full, 1);
+    mbar_init(bars, 1);
     for (int s = 0; s < 2; ++s) {
-      mbar_init(&k_full[s], 1);
-      mbar_init(&k_empty[s], 1);
-      mbar_init(&v_full[s], 1);
-      mbar_init(&v_empty[s], 1);
-      mbar_init(&s_full[s], 1);
-      mbar_init(&s_free[s], 4);
-      mbar_init(&p_full[s], 4);
-      mbar_init(&pv_done[s], 1);
+      mbar_init(bars + 1 + s, 1);     // kv_full
+      mbar_init(bars + 3 + s, 4);     // p_full: one arrival per softmax warp
+      mbar_init(bars + 5 + s, 1);     // done
     }
     fence_barrier_init();
   }
@@ -187,102 +252,61 @@ __global__ void __launch_bounds__(A_THREADS, AttnCfg<BK, PT>::kMinCtas)
 
   if (warp == 4) {
     if (elect_one()) {
-      mbar_expect_tx(q_full, A_Q_BYTES);
-      tma_load_3d(smem, &map_q, q_full, 0, q0, plane);
-      auto load_k = [&](int j) {
-        const int s = j & 1;
-        mbar_wait(&k_empty[s], ((j >> 1) & 1) ^ 1);
-        mbar_expect_tx(&k_full[s], C::kKTx);
-        tma_load_3d(smem + C::kOffK + s * C::kKSlot, &map_k, &k_full[s], 0, j * BK, kv_plane);
-      };
-      auto load_v = [&](int j) {
-        const int s = j & 1;
-        mbar_wait(&v_empty[s], ((j >> 1) & 1) ^ 1);
-        mbar_expect_tx(&v_full[s], C::kVtBytes);
+      mbar_expect_tx_addr(q_full, A_Q_BYTES + (nkt > 1 ? 2 : 1) * C::kKTx);
+      tma_load_3d_addr(sbase, &map_q, q_full, 0, q0, plane);
+      tma_load_3d_addr(sbase + C::kOffK, &map_k, q_full, 0, 0, kv_plane);
+      if (nkt > 1) tma_load_3d_addr(sbase + C::kOffK + C::kKSlot, &map_k, q_full, 0, BK, kv_plane);
+      // refill g: V^T(g) and K(g+2) into slot g & 1 once done[g & 1] has completed g/2 + 1 times
+      for (int g = 0; g < nkt; ++g) {
+        const uint32_t s = g & 1;
+        const bool has_k = g + 2 < nkt;
+        mbar_wait_lean(done + s * 8, (g >> 1) & 1);
+        mbar_expect_tx_addr(kv_full + s * 8, C::kVtBytes + (has_k ? C::kKTx : 0));
 #pragma unroll
         for (int kb = 0; kb < C::kNKB; ++kb)
-          tma_load_3d(smem + C::kOffVt + s * C::kVtBytes + kb * (kD * 128), &map_vt, &v_full[s], j * BK + kb * 64, 0,
-                      kv_plane);
-      };
-      // issue order = the order in which the slots become free: S(j) is issued two tiles ahead of P V(j)
-      load_k(0);
-      if (nkt > 1) load_k(1);
-      for (int j = 0; j < nkt; ++j) {
-        if (j + 2 < nkt) load_k(j + 2);
-        load_v(j);
+          tma_load_3d_addr(sbase + C::kOffVt + s * C::kVtBytes + kb * (kD * 128), &map_vt, kv_full + s * 8,
+                           g * BK + kb * 64, 0, kv_plane);
+        if (has_k) tma_load_3d_addr(sbase + C::kOffK + s * C::kKSlot, &map_k, kv_full + s * 8, 0, (g + 2) * BK, kv_plane);
       }
     }
   } else if (warp == 5) {
     if (elect_one()) {
       constexpr uint32_t idesc_s = make_idesc(A_BQ, BK);
       constexpr uint32_t idesc_o = make_idesc(A_BQ, kD);
-      const uint32_t sbase = smem_u32(smem);
       const uint64_t qdesc = make_desc(sbase, 512, kSw64);
-      // S(j) = Q K(j)^T into TMEM buffer j & 1; completion arrives on s_full and frees the K slot
-      auto issue_s = [&](int j) {
-        const int s = j & 1;
-        if (!(DBG & 16)) {
-          const uint64_t kdesc = make_desc(sbase + C::kOffK + s * C::kKSlot, 512, kSw64);
+      const uint64_t kdesc0 = make_desc(sbase + C::kOffK, 512, kSw64);
+      const uint64_t vdesc0 = make_desc(sbase + C::kOffVt, 1024, kSw128);
+      // S = Q K^T of the tile whose K sits in slot s, into TMEM buffer s
+      auto issue_s = [&](uint32_t s) {
+        const uint64_t kdesc = kdesc0 + (uint64_t)((s * C::kKSlot) >> 4);
 #pragma unroll
-          for (int k = 0; k < kD / 16; ++k)
-            umma_bf16(tmem + s * BK, qdesc + (uint64_t)(k * 2), kdesc + (uint64_t)(k * 2), idesc_s, k != 0);
-        }
-        umma_commit(&k_empty[s]);
+        for (int k = 0; k < kD / 16; ++k)
+          umma_bf16(tmem + s * BK, qdesc + (uint64_t)(k * 2), kdesc + (uint64_t)(k * 2), idesc_s, k != 0);
       };
-      mbar_wait(q_full, 0);
-      mbar_wait(&k_full[0], 0);
+      mbar_wait_lean(q_full, 0);
       tc_fence_after();
       issue_s(0);
-      umma_commit(&s_full[0]);
+      umma_commit_addr(done);
       if (nkt > 1) {
-        mbar_wait(&k_full[1], 0);
-        tc_fence_after();
         issue_s(1);
-        umma_commit(&s_full[1]);
+        umma_commit_addr(done + 8);
       }
       for (int j = 0; j < nkt; ++j) {
-        const int s = j & 1;
-        const uint32_t ph = (j >> 1) & 1;
-        if (!PT && j + 2 < nkt) {
-          // the TMA wait first: it is long satisfied and must not sit behind the softmax hand-off
-          // K(j+2): completion (j+2)/2 of slot s; S(j) is in the softmax registers: its columns are free
-          mbar_wait2(&k_full[s], ph ^ 1, &s_free[s], ph);
-          tc_fence_after();
-          ATTN_TRACE(2048 + j * 4 + 0);
-          issue_s(j + 2);
-          ATTN_TRACE(2048 + j * 4 + 1);
-        }
-        mbar_wait2(&v_full[s], ph, &p_full[s], ph);      // V^T(j) landed; P(j) is written (shared memory / TMEM)
+        const uint32_t s = j & 1, ph = (j >> 1) & 1;
+        mbar_wait_lean(kv_full + s * 8, ph);      // V^T(j) and K(j+2): landed long ago, off the critical path
+        mbar_wait_lean(p_full + s * 8, ph);       // P(j) is in TMEM buffer s
         tc_fence_after();
-        ATTN_TRACE(2048 + j * 4 + 2);
-        if (!(DBG & 8)) {
-          const uint64_t vdesc = make_desc(sbase + C::kOffVt + s * C::kVtBytes, 1024, kSw128);
-          if (PT) {
+        ATTN_TRACE(4096 + j * 2);
+        const uint64_t vdesc = vdesc0 + (uint64_t)((s * C::kVtBytes) >> 4);
 #pragma unroll
-            for (int k = 0; k < BK / 16; ++k)
-              umma_bf16_ts(tmem_o, tmem + s * BK + k * 8,
-                           vdesc + (uint64_t)((k / 4) * ((kD * 128) >> 4) + (k % 4) * 2), idesc_o, (j | k) != 0);
-          } else {
-            const uint64_t pdesc = make_desc(sbase + C::kOffP + s * C::kPBytes, 1024, kSw128);
-#pragma unroll
-            for (int k = 0; k < BK / 16; ++k)
-              umma_bf16(tmem_o, pdesc + (uint64_t)((k / 4) * ((A_BQ * 128) >> 4) + (k % 4) * 2),
-                        vdesc + (uint64_t)((k / 4) * ((kD * 128) >> 4) + (k % 4) * 2), idesc_o, (j | k) != 0);
-          }
-        }
-        if (PT && j + 2 < nkt) {
-          // S(j+2) overwrites the columns P(j) sits in: issued behind P V(j) (tcgen05 ops of one thread
-          // execute in order)
-          mbar_wait(&k_full[s], ph ^ 1);
-          tc_fence_after();
-          issue_s(j + 2);
-        }
-        // ONE arrival tells the softmax both that S(j+2) is in TMEM buffer s and that P V(j) has
-        // released P buffer s (tcgen05 ops complete in issue order), so its loop waits once per tile
-        if (j + 2 < nkt) umma_commit(&s_full[s]);
-        umma_commit(&v_empty[s]);
-        umma_commit(&pv_done[s]);
-        ATTN_TRACE(2048 + j * 4 + 3);
+        for (int k = 0; k < BK / 16; ++k)
+          umma_bf16_ts(tmem_o, tmem + s * BK + k * 8, vdesc + (uint64_t)((k / 4) * ((kD * 128) >> 4) + (k % 4) * 2),
+                       idesc_o, (j | k) != 0);
+        // S(j+2) overwrites the columns P(j) sits in: issued behind P V(j) (tcgen05 ops of one thread
+        // execute in order)
+        if (j + 2 < nkt) issue_s(s);
+        umma_commit_addr(done + s * 8);
+        ATTN_TRACE(4096 + j * 2 + 1);
       }
     }
   } else {
@@ -290,13 +314,12 @@ __global__ void __launch_bounds__(A_THREADS, AttnCfg<BK, PT>::kMinCtas)
     const int r = warp * 32 + lane;
     const uint32_t lane_off = (uint32_t)(warp * 32) << 16;
     const float c = 0.17677669529663687f * 1.4426950408889634f;   // log2(e)/sqrt(d)
-    const int rsw = r & 7;
-    const uint32_t prow_s = smem_u32(smem) + C::kOffP + r * 128;
     // m_ref is the score the exponent of this row is measured from.  It only follows the running
     // maximum when that has grown by more than kTau (log2 units): p = 2^((s - m_ref) c) then stays
     // below 2^kTau, which fp32 sums and bf16 P hold without loss, and the round trip that rescales O
     // in TMEM (needed on nearly every tile otherwise) becomes rare after the first tiles.
     constexpr float kSumLimit = 256.0f;          // 2^kTau, kTau = 8
+    constexpr float kMasked = -1.0e30f;          // a key past n_kv: 2^x of it is 0 (MUFU) or 2^-100 (polynomial), V^T is 0 there
     constexpr int kNP = BK / 2;                  // pairs of keys per row and tile
     constexpr int kAhead = 4;                    // pairs whose scaled argument is ready ahead of their ex2
     constexpr int kBehind = 5;                   // pairs whose ex2 is in flight before the first consumer reads one
@@ -306,63 +329,58 @@ __global__ void __launch_bounds__(A_THREADS, AttnCfg<BK, PT>::kMinCtas)
     for (int j = 0; j < nkt; ++j) {
       const int sb = j & 1;
       const uint32_t tmem_s = tmem + sb * BK + lane_off;
-      const uint32_t pbuf = prow_s + sb * C::kPBytes;
       const int valid = p.n_kv - j * BK;         // keys of this tile that exist
+      // S(j) is in TMEM (and P V(j-2) has drained buffer sb).  Usually the probe made at the end of the
+      // previous tile has already said so.
       if (threadIdx.x == 0) ATTN_TRACE(j * 8 + 0);
-      // S(j) is in TMEM and P buffer sb is free (P V(j-2) done).  Usually the probe made at the end of
-      // the previous tile has already said so.
-      if (!next_ready) mbar_wait(&s_full[sb], (j >> 1) & 1);
+      if (!next_ready) mbar_wait_lean(done + sb * 8, (j >> 1) & 1);
       tc_fence_after();
       if (threadIdx.x == 0) ATTN_TRACE(j * 8 + 1);
+      // S(j) starts its way into the registers; under its latency the hand-off of the PREVIOUS tile is
+      // finished: P(j-1) is in TMEM (wait::st) -> one arrival per warp on p_full
+      tmem_ld_cols<BK>(tmem_s, sv);
+      if (j > 0) {
+        tmem_st_wait();
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(p_full + (sb ^ 1) * 8) : "memory");
+      }
       // the whole row of S into registers (masking the keys a partial last tile does not have)
-      auto load_row = [&]() {
-        tmem_ld_cols<BK>(tmem_s, sv);
+      auto load_row = [&](bool issue) {
+        if (issue) tmem_ld_cols<BK>(tmem_s, sv);
         tmem_ld_wait();
         if (valid < BK) {
 #pragma unroll
           for (int i = 0; i < BK; ++i)
-            if (i >= valid) sv[i] = 0xff800000u;
+            if (i >= valid) sv[i] = __float_as_uint(kMasked);
         }
       };
-      // One software-pipelined sweep over the row, written so that a lone warp keeps the MUFU pipe fed:
-      // step k scales pair k+kAhead (FFMA2), starts the two ex2 of pair k, and retires pair k-kBehind
-      // (row sum FADD2, bf16 pack F2FP, every fourth pair a 16-byte store into the 128B-swizzled A
-      // tile of the PV MMA: 8 keys = one chunk of the row's 128 B k-block line, chunk index XOR
-      // (row & 7)).  Values are transformed in place: s -> x -> p.  No row maximum is tracked here.
+      // One software-pipelined sweep over the row: step k scales pair k+kAhead (FFMA2), starts the
+      // exponentials of pair k (two MUFU.EX2, or the packed polynomial), and retires pair k-kBehind
+      // (row sum FADD2, bf16 pack F2FP, in place: slot k of sv then holds the packed pair).  Values are
+      // transformed in place: s -> x -> p.  No row maximum is tracked here.
       const uint64_t c2 = pack_f32x2(c, c);
       auto sweep = [&](float mc) -> float {
         const uint64_t nmc2 = pack_f32x2(-mc, -mc);
         uint64_t lsum2 = 0ull;                                // (0.f, 0.f)
-        uint32_t pk[4];
         auto scale = [&](int k) {
-          const float sa = __uint_as_float(sv[2 * k]), sb2 = __uint_as_float(sv[2 * k + 1]);
           float xa, xb;
-          unpack_f32x2(fma_f32x2(pack_f32x2(sa, sb2), c2, nmc2), xa, xb);
+          unpack_f32x2(fma_f32x2(pack_f32x2(__uint_as_float(sv[2 * k]), __uint_as_float(sv[2 * k + 1])), c2, nmc2), xa, xb);
           sv[2 * k] = __float_as_uint(xa);
           sv[2 * k + 1] = __float_as_uint(xb);
         };
         auto expo = [&](int k) {
-          const float xa = __uint_as_float(sv[2 * k]), xb = __uint_as_float(sv[2 * k + 1]);
-          const float a = (DBG & 1) ? xa : poly_sel((2 * k) & 31, PN) ? poly_exp2(xa) : fast_exp2(xa);
-          const float b = (DBG & 1) ? xb : poly_sel((2 * k + 1) & 31, PN) ? poly_exp2(xb) : fast_exp2(xb);
-          sv[2 * k] = __float_as_uint(a);
-          sv[2 * k + 1] = __float_as_uint(b);
+          if (poly_pair(k, PP, kNP)) {
+            poly_exp2_pair(sv[2 * k], sv[2 * k + 1]);
+          } else {
+            sv[2 * k] = __float_as_uint(fast_exp2(__uint_as_float(sv[2 * k])));
+            sv[2 * k + 1] = __float_as_uint(fast_exp2(__uint_as_float(sv[2 * k + 1])));
+          }
         };
         auto retire = [&](int k) {
           const float a = __uint_as_float(sv[2 * k]), b = __uint_as_float(sv[2 * k + 1]);
           lsum2 = add_f32x2(lsum2, pack_f32x2(a, b));
-          if (PT) {
-            // packed in place: slot k belonged to pair k / 2, retired no later than this one
-            sv[k] = pack_bf16x2(a, b);
-            return;
-          }
-          pk[k & 3] = pack_bf16x2(a, b);
-          if ((k & 3) == 3) {
-            const int c16 = k >> 2;                           // 16-byte chunk of the row: keys 8*c16 .. +7
-            const uint32_t kb = pbuf + (c16 >> 3) * (A_BQ * 128);
-            if (!(DBG & 4)) st_shared_v4(kb + (((c16 & 7) ^ rsw) << 4), pk[0], pk[1], pk[2], pk[3]);
-            else if (pk[0] == 0x12345678u) l_run += 1.f;     // keep the values alive
-          }
+          sv[k] = pack_bf16x2(a, b);       // slot k belonged to pair k / 2, retired no later than this one
         };
 #pragma unroll
         for (int k = 0; k < kAhead; ++k) scale(k);
@@ -388,25 +406,24 @@ __global__ void __launch_bounds__(A_THREADS, AttnCfg<BK, PT>::kMinCtas)
         }
         return fmaxf(fmaxf(mx0, mx1), fmaxf(mx2, mx3));
       };
-      if (!(DBG & 2)) load_row();
+      load_row(false);
       if (threadIdx.x == 0) ATTN_TRACE(j * 8 + 2);
       if (j == 0) m_ref = row_max();             // first tile: the reference is the true maximum of the tile
-      if (threadIdx.x == 0) ATTN_TRACE(j * 8 + 3);
       // Later tiles: exponentials are taken against the reference of the earlier tiles, and no maximum
       // is computed at all: a score more than kTau (log2 units) above the reference shows up as a row
       // sum above 2^kTau (p <= sum p; inf and NaN fail the comparison too).  Only then — rare: the
       // running maximum of n keys moves ~ log n times, and a sum that merely crowds the limit just
       // refreshes the reference — is the true maximum taken and the sweep repeated.  S was consumed in
-      // place, so the repeat reads it from TMEM again: the S columns are handed back to the MMA warp
-      // only after the decision (S is double buffered: no one is waiting).
+      // place, so the repeat reads it from TMEM again: P only overwrites the S columns after the decision.
       float lsum = sweep(m_ref * c);
       // early probe of the next tile's S: consumed at the top of the next iteration
-      const bool probe = j + 1 < nkt && mbar_test(&s_full[sb ^ 1], ((j + 1) >> 1) & 1);
-      const bool moved = !(lsum <= kSumLimit) && !(DBG & 32);
+      const bool probe = j + 1 < nkt && mbar_test_addr(done + (sb ^ 1) * 8, ((j + 1) >> 1) & 1);
+      if (threadIdx.x == 0) ATTN_TRACE(j * 8 + 3);
+      const bool moved = !(lsum <= kSumLimit);
       const bool any_moved = __any_sync(0xffffffffu, moved);   // tcgen05.ld is warp-collective
       float alpha = 1.0f;
       if (any_moved) {
-        load_row();
+        load_row(true);
         if (moved) {
           const float mx = fmaxf(row_max(), m_ref);
           alpha = fast_exp2((m_ref - mx) * c);
@@ -414,17 +431,13 @@ __global__ void __launch_bounds__(A_THREADS, AttnCfg<BK, PT>::kMinCtas)
         }
         lsum = sweep(m_ref * c);
       }
-      if (PT) {
-        tmem_st_cols<BK / 2>(tmem_s, sv);          // P(j) over the first half of the S(j) columns
-      } else {
-        tc_fence_before();
-        mbar_arrive_warp(&s_free[sb]);
-      }
+      tmem_st_cols<BK / 2>(tmem_s, sv);          // P(j) over the first half of the S(j) columns
       l_run = l_run * alpha + lsum;
       if (threadIdx.x == 0) ATTN_TRACE(j * 8 + 4);
-      // rescale the running output when some row of this warp moved its reference: needs P V(j-1)
+      // rescale the running output when some row of this warp moved its reference: needs P V(j-1),
+      // i.e. iteration j-1 of the MMA thread = completion (j-1)/2 + 1 of done[(j-1) & 1]
       if (any_moved) {
-        mbar_wait(&pv_done[(j - 1) & 1], ((j - 1) >> 1) & 1);   // j >= 1 here: tile 0 never moves
+        mbar_wait_lean(done + ((j - 1) & 1) * 8, (((j - 1) >> 1) + 1) & 1);   // j >= 1 here: tile 0 never moves
         tc_fence_after();
         uint32_t o[32];
         tmem_ld32(tmem_o + lane_off, o);
@@ -432,18 +445,19 @@ __global__ void __launch_bounds__(A_THREADS, AttnCfg<BK, PT>::kMinCtas)
 #pragma unroll
         for (int i = 0; i < 32; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * alpha);
         tmem_st32(tmem_o + lane_off, o);
-        tmem_st_wait();
       }
-      if (threadIdx.x == 0) ATTN_TRACE(j * 8 + 6);
-      if (PT) tmem_st_wait();
-      else fence_proxy_async();
-      tc_fence_before();
-      mbar_arrive_warp(&p_full[sb]);
+      if (threadIdx.x == 0) ATTN_TRACE(j * 8 + 5);
       next_ready = __all_sync(0xffffffffu, probe);
       if (threadIdx.x == 0) ATTN_TRACE(j * 8 + 7);
     }
+    // hand-off of the last tile
+    tmem_st_wait();
+    tc_fence_before();
+    __syncwarp();
+    if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(p_full + ((nkt - 1) & 1) * 8) : "memory");
     uint32_t v[32];
-    mbar_wait(&pv_done[(nkt - 1) & 1], ((nkt - 1) >> 1) & 1);   // tcgen05 ops complete in order: covers all P V
+    // the last iteration of the MMA thread: tcgen05 ops complete in order, so this covers all P V
+    mbar_wait_lean(done + ((nkt - 1) & 1) * 8, (((nkt - 1) >> 1) + 1) & 1);
     tc_fence_after();
     tmem_ld32(tmem_o + lane_off, v);
     tmem_ld_wait();
@@ -473,20 +487,33 @@ __global__ void __launch_bounds__(A_THREADS, AttnCfg<BK, PT>::kMinCtas)
   }
 }
 
-template <int BK, int PN, int DBG, bool PT>
-void launch_attn_t(const CUtensorMap& mq, const CUtensorMap& mk, const CUtensorMap& mvt, const AttnArgs& a, dim3 grid,
-                   cudaStream_t st) {
-  using C = AttnCfg<BK, PT>;
-  static bool configured = false;
-  if (!configured) {
-    cudaFuncSetAttribute(tc_item_attn_kernel<BK, PN, DBG, PT>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::kSmem);
-    configured = true;
+template <int BK, int PP>
+int launch_attn_t(const CUtensorMap& mq, const CUtensorMap& mk, const CUtensorMap& mvt, const AttnArgs& a, dim3 grid,
+                  cudaStream_t st) {
+  using C = AttnCfg<BK>;
+  static int configured_dev[64] = {0};
+  int dev = 0;
+  cudaGetDevice(&dev);
+  if (dev < 0 || dev >= 64) { set_error("item attention: device index %d out of range", dev); return MMPFN_EUNSUPPORTED; }
+  if (!configured_dev[dev]) {
+    if (cudaFuncSetAttribute(tc_item_attn_kernel<BK, PP>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::kSmem) !=
+        cudaSuccess) {
+      set_error("item attention: cannot opt in to %d bytes of shared memory: %s", C::kSmem,
+                cudaGetErrorString(cudaGetLastError()));
+      return MMPFN_ECUDA;
+    }
+    configured_dev[dev] = 1;
   }
-  tc_item_attn_kernel<BK, PN, DBG, PT><<<grid, A_THREADS, C::kSmem, st>>>(mq, mk, mvt, a);
+  tc_item_attn_kernel<BK, PP><<<grid, A_THREADS, C::kSmem, st>>>(mq, mk, mvt, a);
+  return count_launch();
 }
 
-template <int BK, bool PT>
-int launch_attn_bk(const TcItemAttn& p, int poly, int dbg, cudaStream_t st) {
+}  // namespace
+
+int launch_tc_item_attn(const TcItemAttn& p, cudaStream_t st) {
+  constexpr int BK = 48;
+  if (p.n_q <= 0 || p.B <= 0) return MMPFN_OK;
+  if (p.n_kv <= 0) { set_error("item attention: empty key set"); return MMPFN_EINVAL; }
   const long long planes_q = (long long)p.B * p.T * kH;
   const long long planes_kv = p.shared_kv ? (long long)p.B * p.T : planes_q;
   // stacking pays when it saves tiles; the rows between n_q and Sq_pad of every head are then computed
@@ -517,52 +544,32 @@ int launch_attn_bk(const TcItemAttn& p, int poly, int dbg, cudaStream_t st) {
   }
   AttnArgs a{p.out, p.T, p.n_q, p.n_kv, p.shared_kv, q_tiles, stack ? p.Sq_pad : 0};
   const dim3 grid((unsigned)(grid_planes * q_tiles));
-  if (dbg) {
-    switch (dbg) {
-      case 1: launch_attn_t<BK, 0, 1, PT>(mq, mk, mvt, a, grid, st); break;
-      case 8: launch_attn_t<BK, 0, 8, PT>(mq, mk, mvt, a, grid, st); break;
-      case 63: launch_attn_t<BK, 0, 63, PT>(mq, mk, mvt, a, grid, st); break;
-      case 64: launch_attn_t<BK, 0, 64, PT>(mq, mk, mvt, a, grid, st); break;
-      default: set_error("unknown MMPFN_ATTN_DBG"); return MMPFN_EINVAL;
-    }
-    return count_launch();
+#ifdef MMPFN_DEBUG
+  // tuning builds only (-DMMPFN_DEBUG): MMPFN_ATTN_PP = polynomial pairs of every 24.  The product
+  // library has exactly one variant and reads no environment variable.
+  static int pp = -1;
+  if (pp < 0) {
+    const char* e = getenv("MMPFN_ATTN_PP");
+    pp = e ? atoi(e) : kPolyPairsDefault;
   }
-  switch (poly) {
-    case 4: launch_attn_t<BK, 4, 0, PT>(mq, mk, mvt, a, grid, st); break;
-    case 8: launch_attn_t<BK, 8, 0, PT>(mq, mk, mvt, a, grid, st); break;
-    case 12: launch_attn_t<BK, 12, 0, PT>(mq, mk, mvt, a, grid, st); break;
-    default: launch_attn_t<BK, 0, 0, PT>(mq, mk, mvt, a, grid, st); break;
+  switch (pp) {
+    case 0: return launch_attn_t<BK, 0>(mq, mk, mvt, a, grid, st);
+    case 3: return launch_attn_t<BK, 3>(mq, mk, mvt, a, grid, st);
+    case 4: return launch_attn_t<BK, 4>(mq, mk, mvt, a, grid, st);
+    case 8: return launch_attn_t<BK, 8>(mq, mk, mvt, a, grid, st);
+    case 10: return launch_attn_t<BK, 10>(mq, mk, mvt, a, grid, st);
+    case 12: return launch_attn_t<BK, 12>(mq, mk, mvt, a, grid, st);
+    default: break;
   }
-  return count_launch();
-}
-
-}  // namespace
-
-int launch_tc_item_attn(const TcItemAttn& p, cudaStream_t st) {
-  if (p.n_q <= 0 || p.B <= 0) return MMPFN_OK;
-  if (p.n_kv <= 0) { set_error("item attention: empty key set"); return MMPFN_EINVAL; }
-  // MMPFN_ATTN_POLY (0..16, read once): how many of every 32 exponentials leave the MUFU pipe for
-  // the FMA-pipe polynomial; MMPFN_ATTN_BK: keys per tile (112 or 48).  Defaults = measured optimum.
-  static int poly = -1, dbg = 0, bk = 48, pt = 1;
-  if (poly < 0) {
-    const char* e = getenv("MMPFN_ATTN_POLY");
-    poly = e ? atoi(e) : kAttnPolyDefault;
-    e = getenv("MMPFN_ATTN_DBG");
-    dbg = e ? atoi(e) : 0;
-    e = getenv("MMPFN_ATTN_BK");
-    bk = e ? atoi(e) : 48;
-    e = getenv("MMPFN_ATTN_PT");          // 0: P through shared memory (the older hand-off), A/B timing only
-    pt = e ? atoi(e) : 1;
-  }
-  if (bk == 112) return pt ? launch_attn_bk<112, true>(p, poly, dbg, st) : launch_attn_bk<112, false>(p, poly, dbg, st);
-  if (!pt) return launch_attn_bk<48, false>(p, poly, dbg, st);
-  return launch_attn_bk<48, true>(p, poly, dbg, st);
+#endif
+  return launch_attn_t<BK, kPolyPairsDefault>(mq, mk, mvt, a, grid, st);
 }
 
 }  // namespace mmpfn
 
-// debug: copy the clock64 trace of the traced CTA to the host (MMPFN_ATTN_DBG=64 runs)
+#ifdef MMPFN_DEBUG
 extern "C" int mmpfn_debug_attn_trace(long long* host_out, int n) {
-  if (n > 4096) n = 4096;
+  if (n > 8192) n = 8192;
   return cudaMemcpyFromSymbol(host_out, mmpfn::g_attn_trace, sizeof(long long) * n) == cudaSuccess ? 0 : MMPFN_ECUDA;
 }
+#endif

@@ -5,8 +5,8 @@ it never uses on the hot path (``model/transformer.py:19-20``) and calls scikit-
 newer releases renamed (``utils.py:484-495, 538-544, 557-567``).  This shim is what SURVEY.md
 Appendix C describes; it edits nothing under ``/root/reference``.
 
-Used only by ``oracle/make_golden.py`` and by tests that are skipped when the reference is
-absent.
+Used only by the ``oracle/make_golden*.py`` generators, by tests that are skipped when the
+reference is absent, and by ``bench.py``'s reference arms (the baseline being timed).
 """
 from __future__ import annotations
 
@@ -14,7 +14,20 @@ import os
 import sys
 import types
 
-REFERENCE_ROOT = os.environ.get("MMPFN_REFERENCE_ROOT", "/root/reference")
+_HERE = os.path.dirname(os.path.abspath(__file__))
+
+
+def _find_root() -> str:
+    """``/root/reference`` in the build container; on the GPU box the unmodified snapshot that
+    ``oracle/snapshot_ref.py`` put under the git-ignored ``oracle/_ref/``."""
+    cands = [os.environ.get("MMPFN_REFERENCE_ROOT"), "/root/reference", os.path.join(_HERE, "_ref")]
+    for c in cands:
+        if c and os.path.isdir(os.path.join(c, "mmpfn", "models", "mmpfn")):
+            return c
+    return "/root/reference"
+
+
+REFERENCE_ROOT = _find_root()
 
 
 def reference_available() -> bool:
@@ -92,3 +105,42 @@ def load_reference_model(state_dict, config, *, mixer_type="MGM+CAP", mgm_heads=
     if outlier_std is not None:
         update_encoder_outlier_params(model, outlier_std, model_seed, inplace=True)
     return model, path
+
+
+_DIAG_MARK = "correlation_matrix_avg"
+
+
+class without_diagnostic_loop:
+    """Context manager: run the reference's own ``PerFeatureTransformer._forward`` with the
+    result-neutral diagnostic block ``model/transformer.py:809-813`` removed (T^2 ``torch.mm`` +
+    ``.item()`` host syncs over ``[S,192]x[192,S]``; SURVEY.md gotcha 1 — it makes the 10k/50k-row
+    shapes impossible).  The method's source is read at run time, the five statements that build
+    ``correlation_matrix_avg`` are dropped, and the result is compiled in the reference module's own
+    namespace — every other line of ``_forward`` stays the reference's.  Nothing is written anywhere.
+    """
+
+    def __enter__(self):
+        import inspect
+        import textwrap
+        install()
+        import mmpfn.models.mmpfn.model.transformer as TR
+        self._cls = TR.PerFeatureTransformer
+        self._orig = self._cls._forward
+        src = textwrap.dedent(inspect.getsource(self._orig)).split("\n")
+        start = [i for i, ln in enumerate(src) if ln.strip().startswith(_DIAG_MARK + " = np.zeros")]
+        assert len(start) == 1, "diagnostic block not found where transformer.py:809 has it"
+        i0 = start[0]
+        assert src[i0 + 1].strip().startswith("for i in range(") and src[i0 + 2].strip().startswith("for j in range(") \
+            and src[i0 + 3].strip().startswith(_DIAG_MARK + "[i][j] = torch.mm("), "unexpected diagnostic block"
+        body = src[:i0] + src[i0 + 4:]
+        assert not any(_DIAG_MARK in ln and not ln.strip().startswith("#") for ln in body), \
+            "correlation_matrix_avg is used outside the block"
+        ns = dict(vars(TR))
+        exec(compile("from __future__ import annotations\n" + "\n".join(body), TR.__file__ + ":<_forward minus 809-813>",
+                     "exec"), ns)
+        self._cls._forward = ns["_forward"]
+        return self
+
+    def __exit__(self, *a):
+        self._cls._forward = self._orig
+        return False

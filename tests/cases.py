@@ -39,3 +39,65 @@ def clf_case(name):
 
 def t(x):
     return None if x is None else torch.as_tensor(x)
+
+
+# ---- large-config cases (oracle/make_golden_large.py) ---------------------------------------------------
+CTX10K_GEOM = Geometry(mgm_heads=8, cap_heads=8)
+CTX10K_WSEED = 1
+CTX10K_N_TEST = 256
+CTX10K_KV_ROWS = np.arange(0, 10_000, 625)          # 16 train rows whose cached K/V are kept
+
+
+def ctx10k_inputs():
+    """BASELINE configs[2] shape (10 000 train rows, 64 features, [N,2,768] image+text embeddings) for ONE
+    estimator: a 65th uniform column stands where the reference's fingerprint feature would
+    (model/preprocessing.py:476-523) so that F'=65 -> T=42; 256 seeded test rows."""
+    d = make_dataset("img_text_10k", 0)
+    rng = np.random.default_rng(42)
+    pick = np.sort(rng.choice(len(d["y_test"]), CTX10K_N_TEST, replace=False))
+    fp_tr = rng.random((len(d["y_train"]), 1), dtype=np.float32)
+    fp_te = rng.random((len(d["y_test"]), 1), dtype=np.float32)
+    return dict(X_train=np.concatenate([d["X_train"], fp_tr], 1), img_train=d["img_train"],
+                y_train=d["y_train"].astype(np.float32),
+                X_test=np.concatenate([d["X_test"], fp_te], 1)[pick], img_test=d["img_test"][pick],
+                X_test_all=np.concatenate([d["X_test"], fp_te], 1), img_test_all=d["img_test"], pick=pick,
+                n_classes=d["n_classes"])
+
+
+LAYER50K_GEOM = Geometry(mgm_heads=2, cap_heads=4, nlayers=1)
+LAYER50K_WSEED = 3
+LAYER50K_SSEED = 9
+LAYER50K_QKV_GAIN = 3.0          # scores spread over several units: the softmax is far from uniform over 50k keys
+LAYER50K_SHAPE = (50_000, 128, 3)                   # train rows, test rows, tokens
+LAYER50K_ROWS = np.concatenate([np.arange(0, 50_000, 50_000 // 64)[:64], 50_000 + np.arange(0, 128, 2)])
+
+
+def layer_state(S, T, seed):
+    """A LayerNorm-scaled token state [S, T, 192] (what a layer sees between sublayers)."""
+    rng = np.random.default_rng(seed)
+    x = rng.standard_normal((S, T, 192)).astype(np.float32)
+    x -= x.mean(-1, keepdims=True)
+    x /= x.std(-1, keepdims=True)
+    return x
+
+
+def softmax_np(z):
+    z = z - z.max(-1, keepdims=True)
+    e = np.exp(z)
+    return e / e.sum(-1, keepdims=True)
+
+
+def check_proba(p, pr, tol, what):
+    """BASELINE.json north_star gate: max |dp| <= tol, and argmax agreement reported in full — every
+    disagreeing row must be one the tolerance cannot decide (reference top-2 margin below twice the
+    measured deviation).  Returns (max |dp|, agreement)."""
+    dp = float(np.abs(p - pr).max())
+    flips = np.nonzero(p.argmax(-1) != pr.argmax(-1))[0]
+    srt = np.sort(pr, -1)
+    margin = srt[..., -1] - srt[..., -2]
+    agree = 1.0 - len(flips) / p.shape[0]
+    print(f"[{what}] max|dp| {dp:.3e} (tol {tol:g}); argmax agreement {agree:.4%}; "
+          f"undecided rows (reference margin): {[(int(i), float(margin[i])) for i in flips[:8]]}")
+    assert dp <= tol, (what, dp)
+    assert all(margin[i] <= 2 * dp for i in flips), (what, [(int(i), float(margin[i])) for i in flips])
+    return dp, agree

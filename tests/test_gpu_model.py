@@ -10,7 +10,7 @@ import torch
 from multimodalpfn_b200.model import B200PerFeatureTransformer
 from oracle import forward_ref as R
 from oracle.make_golden import CLF_CASES, MODEL_CASES
-from tests.cases import clf_case, load_golden, model_case, t
+from tests.cases import check_proba, clf_case, load_golden, model_case, t
 
 pytestmark = pytest.mark.gpu
 
@@ -40,17 +40,18 @@ def test_model_joint_vs_golden(name, precision):
     assert logits.shape == g["logits"].shape
     n_cls = 3
     p, pg = softmax_np(logits[:, :n_cls] / 0.9), softmax_np(g["logits"][:, :n_cls] / 0.9)
-    dp = np.abs(p - pg).max()
     if name == "stress_tiny":
-        # logits up to +-10: fp32 still has to agree tightly; bf16 is reported, not gated (gotcha 9)
-        if precision == "fp32":
-            assert dp < 2e-4, dp
-            assert (p.argmax(1) == pg.argmax(1)).all()
+        # trained-like confidence (logits up to +-10, SURVEY.md gotcha 9): the <=2e-3 bf16 criterion is defined for
+        # the small-scale weights only; here bf16 is gated against the reference's OWN autocast-bf16 deviation from
+        # its fp32 (oracle/make_golden_large.py bf16ref: 3.1e-2 on this case), with full argmax agreement
+        rb = load_golden("ref_bf16_autocast")
+        ref_dp = float(rb["stress_tiny_dp"])
+        tol = 2e-4 if precision == "fp32" else ref_dp
+        dp, agree = check_proba(p, pg, tol, f"stress_tiny {precision} (reference autocast-bf16: {ref_dp:.2e}, "
+                                            f"agreement {float(rb['stress_tiny_argmax_agree']):.2%})")
+        assert agree == 1.0
         return
-    assert dp <= P_TOL[precision], dp
-    margin = np.sort(pg, 1)
-    decided = (margin[:, -1] - margin[:, -2]) > 4 * P_TOL[precision]
-    assert (p.argmax(1)[decided] == pg.argmax(1)[decided]).all()
+    check_proba(p, pg, P_TOL[precision], f"{name} {precision}")
     if precision == "fp32":
         assert np.abs(logits - g["logits"]).max() < 5e-5
 
@@ -151,10 +152,10 @@ def test_pad_ufes_shape_vs_oracle(precision):
     model = B200PerFeatureTransformer(sd, geom, precision=precision, seed=0)
     logits = _run_joint(model, X, img, y)
     p, pr = softmax_np(logits[:, :6] / 0.9), softmax_np(ref[:, :6] / 0.9)
-    assert np.abs(p - pr).max() <= P_TOL[precision]
-    srt = np.sort(pr, 1)
-    decided = (srt[:, -1] - srt[:, -2]) > 4 * P_TOL[precision]
-    assert (p.argmax(1)[decided] == pr.argmax(1)[decided]).all()
+    rb = load_golden("ref_bf16_autocast")
+    check_proba(p, pr, P_TOL[precision], f"pad_ufes T=27 {precision} (reference autocast-bf16 on mgmcap_8x8_small: "
+                                         f"dp {float(rb['mgmcap_8x8_small_dp']):.2e}, agreement "
+                                         f"{float(rb['mgmcap_8x8_small_argmax_agree']):.2%})")
 
 
 @pytest.mark.parametrize("seed", list(range(8)))

@@ -1,6 +1,7 @@
 """Item-attention kernel alone at the cfg2 train shape: accuracy against a torch fp32 reference on
-a few planes, then CUDA-event timing.  Variants are selected through the environment
-(MMPFN_ATTN_POLY), one process per variant:  python tools/attn_bench.py [n_q n_kv shared_kv]"""
+a few planes, then CUDA-event timing.  Kernel variants exist only in the tuning build
+(MMPFN_DEBUG_LIB=1 MMPFN_ATTN_PP=<polynomial pairs of 24>), one process per variant:
+    python tools/attn_bench.py [n_q n_kv shared_kv scale B T]"""
 import os
 import sys
 
@@ -11,7 +12,8 @@ from multimodalpfn_b200 import _lib
 
 lib = _lib.load()
 dev = torch.device("cuda")
-B, T = 4, 27
+B = int(sys.argv[5]) if len(sys.argv) > 5 else 4
+T = int(sys.argv[6]) if len(sys.argv) > 6 else 27
 n_q = int(sys.argv[1]) if len(sys.argv) > 1 else 2000
 n_kv = int(sys.argv[2]) if len(sys.argv) > 2 else 2000
 shared = int(sys.argv[3]) if len(sys.argv) > 3 else 0
@@ -57,5 +59,5 @@ bb.record()
 torch.cuda.synchronize()
 ms = a.elapsed_time(bb) / 20
 fl = 4.0 * planes * n_q * n_kv * 32
-print(f"poly={os.environ.get('MMPFN_ATTN_POLY', 'default')} n_q={n_q} n_kv={n_kv} shared={shared} scale={scale} "
+print(f"pp={os.environ.get('MMPFN_ATTN_PP', 'default')} B={B} T={T} n_q={n_q} n_kv={n_kv} shared={shared} scale={scale} "
       f"max|err|={err:.3e}  {ms:.4f} ms  {fl / ms / 1e9:.1f} TFLOP/s")

@@ -1,10 +1,11 @@
-"""clock64 timeline of one CTA of the item-attention kernel (MMPFN_ATTN_DBG=64 build variant)."""
+"""clock64 timeline of one CTA of the item-attention kernel — tuning build only:
+    MMPFN_DEBUG_LIB=1 [MMPFN_ATTN_PP=n] python tools/attn_trace.py"""
 import ctypes as C
 import os
 import sys
 
-os.environ["MMPFN_ATTN_DBG"] = "64"
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+os.environ["MMPFN_DEBUG_LIB"] = "1"
 import numpy as np
 import torch
 
@@ -25,17 +26,25 @@ for _ in range(3):
     _lib.check(lib.mmpfn_item_attention_bf16(q.data_ptr(), k.data_ptr(), vt.data_ptr(), B, T, n, pad, n, pad, 0,
                                              out.data_ptr(), st), "attn")
 torch.cuda.synchronize()
-buf = np.zeros(4096, dtype=np.int64)
-fn = lib.mmpfn_debug_attn_trace
+buf = np.zeros(8192, dtype=np.int64)
+fn = C.CDLL(_lib.lib_path()).mmpfn_debug_attn_trace
 fn.argtypes = [C.c_void_p, C.c_int]
 fn.restype = C.c_int
-assert fn(buf.ctypes.data, 4096) == 0
+assert fn(buf.ctypes.data, 8192) == 0
 t0 = buf[0]
-BK = int(os.environ.get("MMPFN_ATTN_BK", "48"))
-nkt = min((n + BK - 1) // BK, 40)
-print("softmax thread 0: per tile [loop top, s_full ok, S in regs, first-tile max done, sweep + P stored, -, rescale done, p_full arrived] (cycles from the CTA's first stamp; slot 5 is unused)")
+nkt = (n + 47) // 48
+print("softmax thread 0 per tile: deltas [wait done, S in regs, sweep, P st issued, st waited, arrived, vote] | tile total")
+tot = []
 for j in range(nkt):
-    print(j, [int(x - t0) for x in buf[j * 8:j * 8 + 8]], "tile", int(buf[j * 8 + 7] - buf[j * 8]))
-print("mma thread: per tile [-, -, p_full ok, PV (+ S(j+2)) issued and committed]  (slots 0-1 only with P through shared memory)")
-for j in range(nkt):
-    print(j, [int(x - t0) if x else None for x in buf[2048 + j * 4:2048 + j * 4 + 4]])
+    s = buf[j * 8:j * 8 + 8].copy()
+    s[6] = s[5]            # (the hand-off now happens at the top of the next tile, under its TMEM load)
+    nxt = buf[(j + 1) * 8] if j + 1 < nkt else s[7]
+    d = [int(s[i + 1] - s[i]) for i in range(7)]
+    tot.append(int(nxt - s[0]))
+    if j < 12 or j >= nkt - 3:
+        print(j, int(s[0] - t0), d, "| tile", int(nxt - s[0]))
+print("median tile", int(np.median(tot[2:-2])), "cycles")
+print("mma thread per tile: [P ready at, issue+commit took] and lag from softmax arrive to P-ready")
+for j in list(range(8)) + [nkt - 2, nkt - 1]:
+    a, b = buf[4096 + j * 2], buf[4096 + j * 2 + 1]
+    print(j, int(a - t0), int(b - a), "lag from next loop top", int(a - buf[(j + 1) * 8]) if j + 1 < nkt else None)
