@@ -231,6 +231,11 @@ int mmpfn_mlp_bf16(float* state_f32, uint16_t* state_bf16, const uint16_t* w1, c
 int mmpfn_item_attention_bf16(const uint16_t* q, const uint16_t* k, const uint16_t* vt, int B, int T, int n_q,
                               int Sq_pad, int n_kv, int Skv_pad, int shared_kv, uint16_t* out, void* stream);
 
+/* Feature-axis attention alone (layer.py:332-339: per table row, 6 heads over the row's T tokens, d = 32), bf16
+ * tensor-core kernel, for unit tests and HBM-roofline timing.
+ *   qkv [n_rows*T][576] bf16 (q | k | v, head-major inside each third)  ->  att [n_rows*T][192] bf16 */
+int mmpfn_feature_attention_bf16(const uint16_t* qkv, uint16_t* att, long long n_rows, int T, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

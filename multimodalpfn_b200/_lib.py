@@ -73,6 +73,7 @@ SIGNATURES = {
                                     c_void_p, c_void_p, c_void_p]),
     "mmpfn_linear_ln_bf16": (c_int, [c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_void_p]),
     "mmpfn_mlp_bf16": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_void_p]),
+    "mmpfn_feature_attention_bf16": (c_int, [c_void_p, c_void_p, c_ll, c_int, c_void_p]),
     "mmpfn_item_attention_bf16": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int,
                                           c_int, c_void_p, c_void_p]),
 }
@@ -96,6 +97,9 @@ def load(build_if_missing: bool = True):
         except Exception as exc:  # no nvcc on this machine: use the shipped .so if there is one
             if not os.path.exists(path):
                 raise RuntimeError(f"libmmpfn_b200.so is missing and could not be built: {exc}") from exc
+            import warnings
+            warnings.warn(f"{os.path.basename(path)} is older than its sources and could not be rebuilt ({exc}); "
+                          "loading the stale library", RuntimeWarning, stacklevel=2)
     if not os.path.exists(path):
         raise RuntimeError(f"{path} not found — run `python -m multimodalpfn_b200.build`; there is no fallback path")
     lib = C.CDLL(path)

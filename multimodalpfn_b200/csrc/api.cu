@@ -41,24 +41,22 @@ int check_geometry(const mmpfn_geometry* g) {
   return MMPFN_OK;
 }
 
-static int g_dev_ok = -1;
+// the verdict is per device (0 unknown, 1 supported, 2 not): a process may use several
 static int require_device() {
-  if (g_dev_ok < 0) {
+  static signed char ok[64] = {0};
+  static int n_dev = -1;
+  if (n_dev < 0) {
     int n = 0;
-    if (cudaGetDeviceCount(&n) != cudaSuccess || n == 0) {
-      cudaGetLastError();
-      g_dev_ok = 0;
-    } else {
-      int dev = 0;
-      cudaGetDevice(&dev);
-      g_dev_ok = mmpfn_device_supported(dev);
-    }
+    if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); n = 0; }
+    n_dev = n;
   }
-  if (!g_dev_ok) {
-    set_error("no sm_100 CUDA device: libmmpfn_b200 has no CPU fallback");
-    return MMPFN_ENODEVICE;
+  const int dev = n_dev > 0 ? current_device() : -1;
+  if (dev >= 0 && dev < 64) {
+    if (!ok[dev]) ok[dev] = mmpfn_device_supported(dev) ? 1 : 2;
+    if (ok[dev] == 1) return MMPFN_OK;
   }
-  return MMPFN_OK;
+  set_error("no sm_100 CUDA device is current: libmmpfn_b200 holds sm_100a code only and has no CPU fallback");
+  return MMPFN_ENODEVICE;
 }
 
 static SgemmParams gemm(const float* A, int lda, const float* W, int ldw, const float* bias, float* C, int ldc, int M,
@@ -92,15 +90,19 @@ static LayerW layer_w(const mmpfn_weights* w, int l) {
 
 static int kv_pad(int n) { return (n + 63) / 64 * 64; }
 
-// K = 192 projections: the persistent kernel (kernels_rowgemm.cu); MMPFN_ROWGEMM=0 selects the
-// one-tile-per-CTA kernel of kernels_tc.cu instead (A/B timing and bisecting only).
+// K = 192 projections: the persistent kernel (kernels_rowgemm.cu).  In the tuning build (-DMMPFN_DEBUG)
+// MMPFN_ROWGEMM=0 selects the one-tile-per-CTA kernel of kernels_tc.cu instead (A/B timing and bisecting);
+// the product library reads no environment variable.
 static int proj_gemm(const TcGemm& g, cudaStream_t st) {
+#ifdef MMPFN_DEBUG
   static int persistent = -1;
   if (persistent < 0) {
     const char* e = getenv("MMPFN_ROWGEMM");
     persistent = e ? atoi(e) : 1;
   }
-  return persistent ? launch_tc_rowgemm(g, st) : launch_tc_gemm(g, st);
+  if (!persistent) return launch_tc_gemm(g, st);
+#endif
+  return launch_tc_rowgemm(g, st);
 }
 
 // workspace carving for the layers
@@ -154,7 +156,9 @@ int mmpfn_device_supported(int dev) {
     cudaGetLastError();
     return 0;
   }
-  return prop.major == 10 ? 1 : 0;
+  // the library carries sm_100a SASS and no PTX: compute capability 10.0 exactly (an sm_103 part would pass a
+  // "major == 10" test and then fail at the first launch)
+  return (prop.major == 10 && prop.minor == 0) ? 1 : 0;
 }
 
 size_t mmpfn_layer_weight_elems(const mmpfn_geometry* g) {
@@ -336,12 +340,16 @@ static int mlp(const LayerW& lw, float* state, uint16_t* state_b, long long M, i
     MMPFN_TRY(launch_sgemm(gemm(ws.hid, kHid, lw.w2, kHid, nullptr, ws.tmp, kE, (int)M, kE, kHid), EPI_NONE, st));
     return launch_layernorm(ws.tmp, state, nullptr, nullptr, M, kE, state, nullptr, st);
   }
-  // MMPFN_FUSED_MLP=0 falls back to the two-GEMM form (A/B timing and bisecting only)
+#ifdef MMPFN_DEBUG
+  // tuning build only: MMPFN_FUSED_MLP=0 takes the two-GEMM form (A/B timing and bisecting)
   static int fused = -1;
   if (fused < 0) {
     const char* e = getenv("MMPFN_FUSED_MLP");
     fused = e ? atoi(e) : 1;
   }
+#else
+  constexpr int fused = 1;
+#endif
   if (fused) {
     TcMlp f{};
     f.state_b = state_b; f.state_b_out = state_b; f.resid_f32 = state; f.w1 = lw.w1_b; f.w2 = lw.w2_b; f.M = (int)M;
@@ -381,10 +389,8 @@ static int check_layers_args(const mmpfn_geometry* g, const mmpfn_weights* w, fl
     set_error("layers: bf16 mode needs the bf16 state shadow and bf16 weights");
     return MMPFN_EINVAL;
   }
-  if ((long long)B * S * T > 2147483647LL / (3 * kE)) {
-    // row counts are passed as int to the GEMM tiles
-    if ((long long)B * S * T > 2147483647LL) { set_error("layers: too many tokens"); return MMPFN_EUNSUPPORTED; }
-  }
+  // row counts are passed as int to the GEMM tiles
+  if ((long long)B * S * T > 2147483647LL) { set_error("layers: too many tokens"); return MMPFN_EUNSUPPORTED; }
   *ws = carve(workspace, (long long)B * S * T, B, S, T, precision);
   if (!workspace || workspace_bytes < ws->bytes) {
     set_error("layers: workspace %zu < %zu bytes", workspace_bytes, ws->bytes);
@@ -703,6 +709,12 @@ int mmpfn_item_attention_bf16(const uint16_t* q, const uint16_t* k, const uint16
   a.q = q; a.k = k; a.vt = vt; a.out = out; a.B = B; a.T = T; a.n_q = n_q; a.Sq_pad = Sq_pad; a.n_kv = n_kv;
   a.Skv_pad = Skv_pad; a.shared_kv = shared_kv;
   return launch_tc_item_attn(a, (cudaStream_t)stream);
+}
+
+int mmpfn_feature_attention_bf16(const uint16_t* qkv, uint16_t* att, long long n_rows, int T, void* stream) {
+  MMPFN_TRY(require_device());
+  if (!qkv || !att || n_rows < 1 || T < 1) { set_error("feature_attention_bf16: bad arguments"); return MMPFN_EINVAL; }
+  return launch_feat_attn_bf16(qkv, att, n_rows, T, (cudaStream_t)stream);
 }
 
 }  // extern "C"

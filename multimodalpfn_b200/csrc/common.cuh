@@ -33,6 +33,40 @@ inline int count_launch() {
   return MMPFN_OK;
 }
 
+// Per-device facts: the library may be called on several devices of one process (one after another or from one
+// host thread per GPU), so nothing about "the" device is cached in a plain static.
+inline int current_device() {
+  int d = 0;
+  if (cudaGetDevice(&d) != cudaSuccess) { cudaGetLastError(); return -1; }
+  return d;
+}
+inline int device_sm_count() {
+  static int n[64] = {0};
+  const int d = current_device();
+  if (d < 0 || d >= 64) return 148;
+  if (!n[d]) {
+    int v = 0;
+    if (cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, d) != cudaSuccess || v < 1) { cudaGetLastError(); v = 148; }
+    n[d] = v;
+  }
+  return n[d];
+}
+// Opt a kernel in to `bytes` of dynamic shared memory, once per device and call site; a failure is reported here
+// (MMPFN_ECUDA with a message) instead of surfacing later as an unexplained launch error.
+#define MMPFN_OPT_IN_SMEM(kern, bytes)                                                                     \
+  do {                                                                                                     \
+    static unsigned long long _done = 0;                                                                   \
+    const int _d = ::mmpfn::current_device();                                                              \
+    if (_d < 0 || _d >= 64 || !((_done >> _d) & 1ull)) {                                                   \
+      if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)(bytes)) != cudaSuccess) { \
+        ::mmpfn::set_error("cannot opt in to %d bytes of dynamic shared memory: %s", (int)(bytes),           \
+                           cudaGetErrorString(cudaGetLastError()));                                        \
+        return MMPFN_ECUDA;                                                                                \
+      }                                                                                                    \
+      if (_d >= 0 && _d < 64) _done |= 1ull << _d;                                                         \
+    }                                                                                                      \
+  } while (0)
+
 #define MMPFN_TRY(expr)            \
   do {                             \
     int _rc = (expr);              \

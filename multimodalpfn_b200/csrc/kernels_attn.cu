@@ -491,19 +491,7 @@ template <int BK, int PP>
 int launch_attn_t(const CUtensorMap& mq, const CUtensorMap& mk, const CUtensorMap& mvt, const AttnArgs& a, dim3 grid,
                   cudaStream_t st) {
   using C = AttnCfg<BK>;
-  static int configured_dev[64] = {0};
-  int dev = 0;
-  cudaGetDevice(&dev);
-  if (dev < 0 || dev >= 64) { set_error("item attention: device index %d out of range", dev); return MMPFN_EUNSUPPORTED; }
-  if (!configured_dev[dev]) {
-    if (cudaFuncSetAttribute(tc_item_attn_kernel<BK, PP>, cudaFuncAttributeMaxDynamicSharedMemorySize, C::kSmem) !=
-        cudaSuccess) {
-      set_error("item attention: cannot opt in to %d bytes of shared memory: %s", C::kSmem,
-                cudaGetErrorString(cudaGetLastError()));
-      return MMPFN_ECUDA;
-    }
-    configured_dev[dev] = 1;
-  }
+  MMPFN_OPT_IN_SMEM((tc_item_attn_kernel<BK, PP>), C::kSmem);
   tc_item_attn_kernel<BK, PP><<<grid, A_THREADS, C::kSmem, st>>>(mq, mk, mvt, a);
   return count_launch();
 }

@@ -261,7 +261,11 @@ int launch_feat_attn(const TIn* qkv, TOut* att, long long n_seq, int T, cudaStre
     return MMPFN_EUNSUPPORTED;
   }
   auto kern = feat_attn_kernel<TIn, TOut>;
-  if (smem > 48 * 1024) cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (smem > 48 * 1024 &&
+      cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) {
+    set_error("feature attention: cannot opt in to %zu bytes of shared memory: %s", smem, cudaGetErrorString(cudaGetLastError()));
+    return MMPFN_ECUDA;
+  }
   // grid.x carries the rows (up to 2^31-1)
   kern<<<dim3((unsigned)n_seq, kH), 128, smem, st>>>(qkv, att, T);
   return count_launch();
@@ -455,15 +459,8 @@ int launch_feat_attn_mma_t(const uint16_t* qkv, uint16_t* att, long long n_seq, 
   const int n_buf = (size_t)2 * Tp * FA_ROW_BYTES <= 200 * 1024 ? 2 : 1;
   const size_t smem = (size_t)n_buf * Tp * FA_ROW_BYTES;
   auto kern = feat_attn_mma_kernel<KT>;
-  static bool configured = false;
-  static int n_sm = 148;
-  if (!configured) {
-    cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024);
-    int dev = 0;
-    cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev);
-    configured = true;
-  }
+  MMPFN_OPT_IN_SMEM(kern, 227 * 1024);
+  const int n_sm = device_sm_count();
   const int n_items = kH * (Tp / 16);
   const int warps = n_items < 12 ? n_items : 12;
   // CTAs resident per SM: shared memory (two staging buffers each) and 2048 threads

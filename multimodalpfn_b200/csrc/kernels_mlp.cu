@@ -98,10 +98,15 @@ __device__ __forceinline__ uint32_t gelu2_bf16(float x0, float x1) {
 }
 
 // DBG = 1: clock64 trace of the MMA thread of CTA 0 (8 stamps per chunk: before / after each wait)
+#ifdef MMPFN_DEBUG
 __device__ long long g_mlp_trace[4096];
+#define MLP_TRACE_BODY(slot) if (DBG && blockIdx.x == 0 && (slot) < 4096) g_mlp_trace[(slot)] = clock64();
+#else
+#define MLP_TRACE_BODY(slot)
+#endif
 #define MLP_TRACE(slot)                                                                    \
   do {                                                                                     \
-    if (DBG && blockIdx.x == 0 && (slot) < 4096) g_mlp_trace[(slot)] = clock64();          \
+    MLP_TRACE_BODY(slot)                                                                   \
   } while (0)
 
 template <int DBG>
@@ -454,30 +459,37 @@ int launch_tc_mlp(const TcMlp& p, cudaStream_t st) {
     const cuuint32_t box[2] = {F_CH, kE};
     MMPFN_TRY(encode_map(&mw2, p.w2, 2, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_128B));
   }
-  static int n_sm = 0, dbg = 0;
-  if (!n_sm) {
-    int dev = 0;
-    cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev);
-    cudaFuncSetAttribute(tc_mlp_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, F_SMEM);
-    cudaFuncSetAttribute(tc_mlp_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, F_SMEM);
-    const char* e = getenv("MMPFN_MLP_DBG");
+  const int n_sm = device_sm_count();
+  MMPFN_OPT_IN_SMEM(tc_mlp_kernel<0>, F_SMEM);
+#ifdef MMPFN_DEBUG
+  MMPFN_OPT_IN_SMEM(tc_mlp_kernel<1>, F_SMEM);
+  static int dbg = -1;
+  if (dbg < 0) {
+    const char* e = getenv("MMPFN_MLP_DBG");          // tuning build only: clock64 trace variant
     dbg = e ? atoi(e) : 0;
   }
+#endif
   MlpArgs a{};
   a.M = p.M;
   a.n_tiles = (p.M + F_BM - 1) / F_BM;
   a.state_b = p.state_b;
   const int grid = a.n_tiles < n_sm ? a.n_tiles : n_sm;
-  if (dbg) tc_mlp_kernel<1><<<grid, F_THREADS, F_SMEM, st>>>(ma, mw1, mw2, mr, my, a);
-  else tc_mlp_kernel<0><<<grid, F_THREADS, F_SMEM, st>>>(ma, mw1, mw2, mr, my, a);
+#ifdef MMPFN_DEBUG
+  if (dbg) {
+    tc_mlp_kernel<1><<<grid, F_THREADS, F_SMEM, st>>>(ma, mw1, mw2, mr, my, a);
+    return count_launch();
+  }
+#endif
+  tc_mlp_kernel<0><<<grid, F_THREADS, F_SMEM, st>>>(ma, mw1, mw2, mr, my, a);
   return count_launch();
 }
 
 }  // namespace mmpfn
 
-// debug: copy the clock64 trace of CTA 0's MMA thread to the host (MMPFN_MLP_DBG=1 runs)
+#ifdef MMPFN_DEBUG
+// tuning build only: copy the clock64 trace of CTA 0's MMA thread to the host (MMPFN_MLP_DBG=1 runs)
 extern "C" int mmpfn_debug_mlp_trace(long long* host_out, int n) {
   if (n > 4096) n = 4096;
   return cudaMemcpyFromSymbol(host_out, mmpfn::g_mlp_trace, sizeof(long long) * n) == cudaSuccess ? 0 : MMPFN_ECUDA;
 }
+#endif

@@ -372,11 +372,7 @@ __global__ void __launch_bounds__(R_THREADS, 1) tc_rowgemm_kernel(const __grid_c
 template <int EPI>
 int launch_rowgemm_t(const CUtensorMap& ma, const CUtensorMap& mw, const CUtensorMap& mr, const CUtensorMap& my,
                      const ItemMaps& im, const RowGemmArgs& a, int grid, cudaStream_t st) {
-  static bool configured = false;
-  if (!configured) {
-    cudaFuncSetAttribute(tc_rowgemm_kernel<EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, R_SMEM);
-    configured = true;
-  }
+  MMPFN_OPT_IN_SMEM(tc_rowgemm_kernel<EPI>, R_SMEM);
   tc_rowgemm_kernel<EPI><<<grid, R_THREADS, R_SMEM, st>>>(ma, mw, mr, my, im, a);
   return count_launch();
 }
@@ -465,12 +461,7 @@ int launch_tc_rowgemm(const TcGemm& p, cudaStream_t st) {
     if (p.k0_out) MMPFN_TRY(rows_map(&im.k0, p.k0_out, planes0));
     if (p.vt0_out) MMPFN_TRY(cols_map(&im.vt0, p.vt0_out, planes0));
   }
-  static int n_sm = 0;
-  if (!n_sm) {
-    int dev = 0;
-    cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev);
-  }
+  const int n_sm = device_sm_count();
   int per_n = n_sm / a.n_tiles;
   if (per_n > a.m_tiles) per_n = a.m_tiles;
   if (per_n < 1) per_n = 1;

@@ -401,7 +401,11 @@ int launch_cap_attn(const float* kv, const float* q, int S, int n_kv, int Hc, fl
     set_error("CAP: %d source tokens x head_dim %d exceed the shared-memory tile", n_kv, hd);
     return MMPFN_EUNSUPPORTED;
   }
-  if (smem > 48 * 1024) cudaFuncSetAttribute(cap_attn_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (smem > 48 * 1024 &&
+      cudaFuncSetAttribute(cap_attn_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) {
+    set_error("CAP: cannot opt in to %zu bytes of shared memory: %s", smem, cudaGetErrorString(cudaGetLastError()));
+    return MMPFN_ECUDA;
+  }
   cap_attn_kernel<<<dim3(S, Hc), 128, smem, st>>>(kv, q, n_kv, Hc, out);
   return count_launch();
 }

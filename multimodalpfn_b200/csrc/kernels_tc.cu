@@ -240,11 +240,7 @@ __global__ void __launch_bounds__(G_THREADS) tc_gemm_kernel(const __grid_constan
 
 template <int EPI>
 int launch_gemm_t(const CUtensorMap& ma, const CUtensorMap& mw, const GemmArgs& a, dim3 grid, cudaStream_t st) {
-  static bool configured = false;
-  if (!configured) {
-    cudaFuncSetAttribute(tc_gemm_kernel<EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, G_SMEM);
-    configured = true;
-  }
+  MMPFN_OPT_IN_SMEM(tc_gemm_kernel<EPI>, G_SMEM);
   tc_gemm_kernel<EPI><<<grid, G_THREADS, G_SMEM, st>>>(ma, mw, a);
   return count_launch();
 }

@@ -91,18 +91,25 @@ class B200InferenceEngine:
         self.img_train_dev = None if self.image_train is None else torch.from_numpy(self.image_train).to(dev)
         self._img_tok_train = None
         self.nan_flag = torch.zeros(1, dtype=torch.int32, device=dev)
-        self._graphs = {}
+        self._graphs = {}                      # input shapes -> (graph, static inputs, static output, scratch epoch)
+        self.max_graphs = 4                    # least recently used beyond that are dropped (each holds a private pool)
         self._pinned_bufs = {}
-        import os
-        self.multi_group = os.environ.get("MMPFN_MULTI_GROUP", "1") != "0"     # 0: one pass per group (A/B timing)
+        self.multi_group = True                # False: one pass per group (tests compare the two, bit for bit)
         self._stage_event = None
         self.launches_per_call = None
         if cache_context:
             self._build_contexts()
 
-    def _build_contexts(self):
+    def train_image_tokens(self):
+        """Image/text tokens of the TRAIN rows: the MGM/CAP stem works row by row and the train embeddings never
+        change between calls (inference.py:272 keeps them as they are), so they are projected once — the
+        reference recomputes them inside every forward (transformer.py:755-761)."""
         if self.img_train_dev is not None and self._img_tok_train is None:
             self._img_tok_train = self.model.stem_image(self.img_train_dev)
+        return self._img_tok_train
+
+    def _build_contexts(self):
+        self.train_image_tokens()
         for g in self.groups:
             g["ctx"] = self.model.fit_context(g["X_train"], None, g["y_train"], img_tok_train=self._img_tok_train,
                                               label_stats=g["label_stats"])
@@ -168,16 +175,14 @@ class B200InferenceEngine:
                 for k, i in enumerate(g["idx"]):
                     out[i] = lg[k]
         elif multi:
-            tok = None
+            tok_tr = tok_te = None
             if img_test_dev is not None:
-                tok = m.stem_image(torch.cat([self.img_train_dev, img_test_dev], dim=0))
-            n_tr = self.groups[0]["y_train"].shape[1]
+                tok_tr, tok_te = self.train_image_tokens(), m.stem_image(img_test_dev)
             specs = [dict(X_train=g["X_train"], y_train=g["y_train"], X_all=torch.cat([g["X_train"], Xte], dim=1),
-                          img_tok_train=None if tok is None else tok[:n_tr], label_stats=g["label_stats"])
+                          img_tok_train=tok_tr, label_stats=g["label_stats"])
                      for g, Xte in zip(self.groups, staged["X_test"])]
             ctxs = m.fit_contexts(specs, nan_flag=flag)
-            lgs = m.predict_with_contexts(ctxs, staged["X_test"], img_tok_test=None if tok is None else tok[n_tr:],
-                                          nan_flag=flag)
+            lgs = m.predict_with_contexts(ctxs, staged["X_test"], img_tok_test=tok_te, nan_flag=flag)
             for g, lg in zip(self.groups, lgs):
                 for k, i in enumerate(g["idx"]):
                     out[i] = lg[k]
@@ -189,17 +194,14 @@ class B200InferenceEngine:
                     out[i] = lg[k]
         else:
             # reference-equivalent: the train context is rebuilt inside every call (inference.py:302-348)
-            tok = None
+            tok_tr = tok_te = None
             if img_test_dev is not None:
-                tok = m.stem_image(torch.cat([self.img_train_dev, img_test_dev], dim=0))
+                tok_tr, tok_te = self.train_image_tokens(), m.stem_image(img_test_dev)
             for g, Xte in zip(self.groups, staged["X_test"]):
-                n_tr = g["y_train"].shape[1]
                 X_full = None if Xte is None else torch.cat([g["X_train"], Xte], dim=1)
-                ctx = m.fit_context(g["X_train"], None, g["y_train"], X_all=X_full,
-                                    img_tok_train=None if tok is None else tok[:n_tr], check=False,
+                ctx = m.fit_context(g["X_train"], None, g["y_train"], X_all=X_full, img_tok_train=tok_tr, check=False,
                                     label_stats=g["label_stats"], nan_flag=flag)
-                lg = m.predict_with_context(ctx, Xte, None, img_tok_test=None if tok is None else tok[n_tr:],
-                                            check=False, nan_flag=flag)
+                lg = m.predict_with_context(ctx, Xte, None, img_tok_test=tok_te, check=False, nan_flag=flag)
                 for k, i in enumerate(g["idx"]):
                     out[i] = lg[k]
         return torch.stack(out)
@@ -216,6 +218,12 @@ class B200InferenceEngine:
         key = (tuple(None if x is None else tuple(x.shape) for x in staged["X_test"]),
                None if staged["img_test"] is None else tuple(staged["img_test"].shape))
         ent = self._graphs.get(key)
+        epoch = getattr(self.model, "scratch_epoch", 0)
+        if ent is not None and ent[3] != epoch:
+            # a scratch buffer of the model was replaced since the capture (a larger batch, another engine or
+            # predict_proba_tasks on the same model): every captured graph points into freed storage
+            self._graphs.clear()
+            ent = None
         if ent is None:
             static = dict(X_test=[None if x is None else x.clone() for x in staged["X_test"]],
                           img_test=None if staged["img_test"] is None else staged["img_test"].clone())
@@ -231,9 +239,17 @@ class B200InferenceEngine:
             with torch.cuda.graph(graph):
                 out = self.logits_staged(static)
             self.launches_per_call = _lib.launch_count() - l0
-            ent = (graph, static, out)
+            # the warm-up may itself have grown the scratch buffers: graphs captured earlier are stale then
+            epoch_now = getattr(self.model, "scratch_epoch", 0)
+            if epoch_now != epoch:
+                self._graphs.clear()
+            ent = (graph, static, out, epoch_now)
             self._graphs[key] = ent
-        graph, static, out = ent
+            while len(self._graphs) > self.max_graphs:
+                self._graphs.pop(next(iter(self._graphs)))
+        else:
+            self._graphs[key] = self._graphs.pop(key)          # most recently used last
+        graph, static, out, _ = ent
         for dst, src in zip(static["X_test"], staged["X_test"]):
             if dst is not None:
                 dst.copy_(src, non_blocking=True)

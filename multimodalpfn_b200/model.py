@@ -76,6 +76,9 @@ class B200PerFeatureTransformer:
         self._w = C.byref(self.w.c_weights)
         self._pos_cache = {}
         self._buf = {}
+        # bumped whenever a shared scratch buffer is replaced (and its old storage freed): CUDA graphs captured
+        # before hold raw pointers into the old storage and must not be replayed (engine.logits_graphed checks)
+        self.scratch_epoch = 0
         # attributes the reference's engine / loader touch
         self.ninp = geom.emsize
         self.features_per_group = geom.features_per_group
@@ -109,7 +112,11 @@ class B200PerFeatureTransformer:
     def _scratch(self, name: str, nbytes: int) -> torch.Tensor:
         t = self._buf.get(name)
         if t is None or t.numel() < nbytes:
+            if torch.cuda.is_current_stream_capturing():
+                raise RuntimeError(f"scratch buffer {name!r} would grow during CUDA-graph capture: warm up first")
             t = torch.empty(max(nbytes, 1), dtype=torch.uint8, device=self.device)
+            if name in self._buf:
+                self.scratch_epoch += 1
             self._buf[name] = t
         return t
 
@@ -236,8 +243,9 @@ class B200PerFeatureTransformer:
 
     def alloc_kv(self, B: int, n_train: int, T: int) -> torch.Tensor:
         nbytes = self.lib.mmpfn_kv_bytes(self._g, B, n_train, T, self.precision)
-        # zero-filled: the bf16 layout pads the row axis to a multiple of 64
-        return torch.zeros(nbytes, dtype=torch.uint8, device=self.device)
+        # not zero-filled: the bf16 layout pads the row axis to a multiple of 64, but every reader goes through a
+        # TMA tensor map whose extent is the true row count (pad rows are never fetched: out-of-bounds zero fill)
+        return torch.empty(nbytes, dtype=torch.uint8, device=self.device)
 
     def merge_kv(self, parts, B: int, n_train: int, T: int) -> torch.Tensor:
         """Assemble the K/V context of a batch of B estimators from contexts built for subsets of it
@@ -437,14 +445,17 @@ class B200PerFeatureTransformer:
             img_tok = self.stem_image(img_full) if img_full is not None else None
             X_tr = None if X_full is None else X_full[:, :n_train].contiguous()
             X_te = None if X_full is None else X_full[:, n_train:].contiguous()
+            # ONE flag for train and test rows: the reference raises on NaN anywhere in the embedded input
+            # (transformer.py:790-796)
+            flag = torch.zeros(1, dtype=torch.int32, device=self.device)
             ctx = self.fit_context(X_tr, None, y_train, X_all=X_full,
                                    img_tok_train=None if img_tok is None else img_tok[:n_train].contiguous(),
-                                   check=False)
+                                   check=False, nan_flag=flag)
             if img_full is not None:
                 ctx.n_tok = img_full.shape[1]
             return self.predict_with_context(ctx, X_te, None,
                                              img_tok_test=None if img_tok is None else img_tok[n_train:].contiguous(),
-                                             check=check)
+                                             check=check, nan_flag=flag)
 
     def __call__(self, *args, only_return_standard_out: bool = True, categorical_inds=None,
                  single_eval_pos: Optional[int] = None, **kwargs):

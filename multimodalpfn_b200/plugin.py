@@ -10,9 +10,10 @@ engine calls at ``inference.py:343-348`` for ``B200PerFeatureTransformer``.
 The patch wraps ``create_inference_engine`` (``base.py:168-257``, called from
 ``classifier.py:485-500``): the engine the reference builds keeps its per-estimator preprocessors
 and tables; its ``.model`` attribute is replaced.  Nothing under the reference tree is edited.
-Needs the reference and an sm_100 GPU in the same process (neither CI box here has both: the GPU
-box has no reference; this container has no GPU), so it is exercised by ``tests/test_plugin_wiring.py``
-with a recording stand-in for the CUDA model.
+Needs the reference and an sm_100 GPU in the same process: ``tests/test_gpu_plugin.py`` runs it on the
+GPU box against the unmodified reference snapshot ``oracle/snapshot_ref.py`` ships there (real
+``MMPFNClassifier``, real CUDA model, compared with the reference's own CPU and CUDA ``predict_proba``);
+``tests/test_plugin_wiring.py`` checks the wiring on CPU with a recording stand-in for the CUDA model.
 """
 from __future__ import annotations
 
@@ -44,18 +45,61 @@ def outlier_std_of(module):
     return None
 
 
-def convert(module, *, device, precision="bf16", model_cls=None):
-    """reference nn.Module -> B200PerFeatureTransformer with the same weights and seed."""
+def convert(module, *, device, precision="bf16", model_cls=None, pos_emb_device="cuda"):
+    """reference nn.Module -> B200PerFeatureTransformer with the same weights and seed.
+
+    ``pos_emb_device``: where the positional noise is drawn.  The reference draws it with a generator on
+    the model's device (``transformer.py:887-892``), and torch's CPU and CUDA generators give different
+    streams: "cuda" reproduces the reference running on the same GPU, "cpu" the reference on the host."""
     if model_cls is None:
         from .model import B200PerFeatureTransformer as model_cls
     sd = {k: v.detach().cpu() for k, v in module.state_dict().items()}
     return model_cls(sd, geometry_of(module), device=device, precision=precision, seed=module.seed,
-                     outlier_std=outlier_std_of(module),
-                     pos_emb_device="cuda")     # the reference draws on the model's device (transformer.py:887-892)
+                     outlier_std=outlier_std_of(module), pos_emb_device=pos_emb_device)
 
 
-def install(precision: str = "bf16", model_cls=None):
-    """Patch ``mmpfn.models.mmpfn.classifier.create_inference_engine``; returns an ``uninstall()``."""
+class B200PluginEngine:
+    """Stands where the reference's ``InferenceEngineCachePreprocessing`` stands (``inference.py:204-351``),
+    built FROM the engine the reference prepared: its fitted per-estimator preprocessors, preprocessed
+    train tables, permuted labels, ensemble configs and train embeddings are taken as they are, so the
+    tensors that reach the model are the reference's.  What changes is how ``iter_outputs``
+    (``inference.py:282-351``) produces its logits: instead of a serial loop of B = 1 forwards it transforms
+    the test table with every estimator's own preprocessor (the reference's code), then runs ALL estimators
+    as one batched CUDA pass (``engine.B200InferenceEngine``) and yields ``(logits[Nte, n_out], config)``
+    per estimator in the reference's order — the rest of ``predict_proba`` (``classifier.py:532-576``) is
+    untouched."""
+
+    def __init__(self, ref_engine, *, device, precision="bf16", pos_emb_device="cuda", model_cls=None,
+                 cache_context=False):
+        import numpy as np
+        from .engine import B200InferenceEngine
+        self.ref = ref_engine
+        self.preprocessors = ref_engine.preprocessors
+        self.ensemble_configs = ref_engine.ensemble_configs
+        self.model = convert(ref_engine.model, device=device, precision=precision, model_cls=model_cls,
+                             pos_emb_device=pos_emb_device)
+        members = [dict(X_train=None if Xt is None else np.asarray(Xt, dtype=np.float32),
+                        y_train=np.asarray(yt, dtype=np.float32), class_perm=None)
+                   for Xt, yt in zip(ref_engine.X_trains, ref_engine.y_trains)]
+        self.engine = B200InferenceEngine(self.model, members, ref_engine.image_train, cache_context=cache_context)
+
+    def iter_outputs(self, X, image_test, *, device=None, autocast=None):
+        import numpy as np
+        X_tests = [None if X is None or m["X_train"] is None else np.asarray(pre.transform(X).X, dtype=np.float32)
+                   for pre, m in zip(self.preprocessors, self.engine.members)]            # inference.py:303
+        logits = self.engine.logits(X_tests, image_test)
+        self.engine.check_nan()                                                             # transformer.py:790-796
+        for lg, cfg in zip(logits, self.ensemble_configs):
+            yield lg, cfg
+
+
+def install(precision: str = "bf16", model_cls=None, pos_emb_device: str = "cuda", mode: str = "engine"):
+    """Patch ``mmpfn.models.mmpfn.classifier.create_inference_engine``; returns an ``uninstall()``.
+
+    ``mode="model"``: the reference's engine keeps its serial per-estimator loop and only its ``.model`` is
+    swapped (one B = 1 CUDA forward per estimator).  ``mode="engine"`` (default): the engine object itself is
+    replaced by ``B200PluginEngine`` (all estimators in one batched pass) — what SURVEY.md section 7 step 1(i)
+    describes.  Both leave every line of the reference's ``fit`` / ``predict_proba`` in charge."""
     import mmpfn.models.mmpfn.classifier as C
 
     orig = C.create_inference_engine
@@ -67,7 +111,11 @@ def install(precision: str = "bf16", model_cls=None):
         engine = orig(**kw)
         dev = kw["device_"]
         if getattr(dev, "type", str(dev)) == "cuda" and hasattr(engine, "model"):
-            engine.model = convert(engine.model, device=dev, precision=precision, model_cls=model_cls)
+            if mode == "engine" and hasattr(engine, "preprocessors") and hasattr(engine, "X_trains"):
+                return B200PluginEngine(engine, device=dev, precision=precision, pos_emb_device=pos_emb_device,
+                                        model_cls=model_cls)
+            engine.model = convert(engine.model, device=dev, precision=precision, model_cls=model_cls,
+                                   pos_emb_device=pos_emb_device)
         return engine
 
     create_inference_engine._mmpfn_b200 = True

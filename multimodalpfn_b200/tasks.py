@@ -118,8 +118,9 @@ def predict_proba_tasks(model: B200PerFeatureTransformer, tasks: Sequence[dict],
                 Xte = torch.from_numpy(np.stack([prepared[i]["test"][e] for i in idx])).to(dev)
                 X_full = torch.cat([Xtr, Xte], dim=1)
             # reference-equivalent joint forward (the stem's constant-column tests see train and test rows)
-            ctx = model.fit_context(Xtr, None, ytr, X_all=X_full, img_tok_train=tok_tr, check=False)
-            lg = model.predict_with_context(ctx, Xte, None, img_tok_test=tok_te)
+            flag = torch.zeros(1, dtype=torch.int32, device=dev)      # one NaN flag for train and test rows
+            ctx = model.fit_context(Xtr, None, ytr, X_all=X_full, img_tok_train=tok_tr, check=False, nan_flag=flag)
+            lg = model.predict_with_context(ctx, Xte, None, img_tok_test=tok_te, nan_flag=flag)
             for k, i in enumerate(idx):
                 logits[i][e] = lg[k]
             del ctx

@@ -19,7 +19,8 @@ Cases
   train call -> per-layer head-0 K/V cache (layers 0 and 11 kept for 16 rows), then logits of 256
   sampled test rows.
 * ``layer50k`` — the 50 000-key axis of configs[3]: ONE ``PerFeatureEncoderLayer`` (the loaded reference
-  module) on a [50 000 + 128 rows, T=3] state, queries chunked through the reference's own
+  module) on a [50 000 + 128 rows, T=3] state, at the reference's own qkv initialisation (``g1``) and with
+  scores nine times larger (``g3``, a sharp softmax), queries chunked through the reference's own
   ``MultiHeadAttention`` (x = a chunk of rows, x_kv = all train rows) — checked here against
   ``layer.forward`` at a small shape first.
 * ``tasks4``  — configs[4]: four independent 800/200-row tasks, model-level logits each.
@@ -113,9 +114,14 @@ def ref_layer_chunked(layer, state, n_train, q_chunk):
     return layer.layer_norms[2](st, allow_inplace=True)
 
 
-def run_layer50k():
+def run_layer50k(which=None):
+    for name in ([which] if which else list(cases.LAYER50K_GAINS)):
+        _run_layer50k(name)
+
+
+def _run_layer50k(name):
     geom = cases.LAYER50K_GEOM
-    model, _ = _load(geom, cases.LAYER50K_WSEED, qkv_gain=cases.LAYER50K_QKV_GAIN)
+    model, _ = _load(geom, cases.LAYER50K_WSEED, qkv_gain=cases.LAYER50K_GAINS[name])
     layer = model.transformer_encoder.layers[0]
     with torch.inference_mode():
         # harness == layer.forward at a small shape (bit for bit)
@@ -130,8 +136,8 @@ def run_layer50k():
         t0 = time.time()
         out = ref_layer_chunked(layer, state, n_tr, q_chunk=1024)[0]
     rows = cases.LAYER50K_ROWS
-    np.savez_compressed(os.path.join(OUT, "large_layer50k.npz"), out_rows=out[rows].numpy().copy())
-    print(f"layer50k: {time.time() - t0:.0f} s", flush=True)
+    np.savez_compressed(os.path.join(OUT, f"large_layer50k_{name}.npz"), out_rows=out[rows].numpy().copy())
+    print(f"layer50k {name}: {time.time() - t0:.0f} s", flush=True)
 
 
 # ---------------------------------------------------------------------------------------------------
@@ -236,7 +242,8 @@ def run_bf16ref():
     np.savez_compressed(os.path.join(OUT, "ref_bf16_autocast.npz"), **out)
 
 
-CASES = dict(tasks4=run_tasks4, bf16ref=run_bf16ref, clf8=run_clf8, layer50k=run_layer50k, ctx10k=run_ctx10k)
+CASES = dict(tasks4=run_tasks4, bf16ref=run_bf16ref, clf8=run_clf8, layer50k=run_layer50k,
+             layer50k_g1=lambda: run_layer50k("g1"), layer50k_g3=lambda: run_layer50k("g3"), ctx10k=run_ctx10k)
 
 
 def main():

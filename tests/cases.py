@@ -67,7 +67,9 @@ def ctx10k_inputs():
 LAYER50K_GEOM = Geometry(mgm_heads=2, cap_heads=4, nlayers=1)
 LAYER50K_WSEED = 3
 LAYER50K_SSEED = 9
-LAYER50K_QKV_GAIN = 3.0          # scores spread over several units: the softmax is far from uniform over 50k keys
+# g1: the reference's own initialisation law (near-uniform softmax over the 50 000 keys); g3: qkv weights x3, i.e.
+# scores x9 (spread over tens of log2 units: a sharp softmax, the running reference of the bf16 kernel moves)
+LAYER50K_GAINS = {"g1": 1.0, "g3": 3.0}
 LAYER50K_SHAPE = (50_000, 128, 3)                   # train rows, test rows, tokens
 LAYER50K_ROWS = np.concatenate([np.arange(0, 50_000, 50_000 // 64)[:64], 50_000 + np.arange(0, 128, 2)])
 

@@ -133,6 +133,10 @@ def test_item_attention_tcgen05(n_q, n_kv, shared, scale):
     q = (torch.randn(planes, qpad, 32, generator=g) * scale).cuda().to(torch.bfloat16)
     k = (torch.randn(kv_planes, kpad, 32, generator=g) * scale).cuda().to(torch.bfloat16)
     vt = torch.randn(kv_planes, 32, kpad, generator=g).cuda().to(torch.bfloat16)
+    # the pad rows of the K / V^T planes are never fetched (the tensor maps end at n_kv: out-of-bounds zero fill),
+    # so the context buffers need no memset: poison them
+    k[:, n_kv:] = float("nan")
+    vt[:, :, n_kv:] = float("nan")
     out = torch.full((B, n_q, T, 192), float("nan"), dtype=torch.bfloat16, device="cuda")
     _lib.check(lib.mmpfn_item_attention_bf16(q.data_ptr(), k.data_ptr(), vt.data_ptr(), B, T, n_q, qpad, n_kv, kpad,
                                              shared, out.data_ptr(), _stream()), "item_attention")
@@ -181,6 +185,23 @@ def test_item_qkv_scatter_tcgen05(B, S, T, n_proj):
         assert (vt[:, :, :S].double() - rv).abs().max().item() < 0.04
         assert (vt[:, :, S:] == 0).all() and (k[:, S:] == 0).all()
         assert torch.equal(k0, k.reshape(B * T, 6, Sp, 32)[:, 0]) and torch.equal(vt0, vt.reshape(B * T, 6, 32, Sp)[:, 0])
+
+
+@pytest.mark.parametrize("n_rows,T", [(1, 1), (7, 3), (300, 20), (515, 27), (64, 42), (33, 90), (9, 127)])
+def test_feature_attention_bf16(n_rows, T):
+    """softmax(q k^T / sqrt 32) v over the T tokens of every table row, 6 heads (layer.py:332-339), mma.sync kernel
+    vs torch fp32 on the same bf16 operands; token counts of every BASELINE config (20/27, 42/90, up to 127)."""
+    lib = _lib.load()
+    g = torch.Generator().manual_seed(n_rows * 131 + T)
+    qkv = torch.randn(n_rows * T, 576, generator=g).cuda().to(torch.bfloat16)
+    att = torch.full((n_rows * T, 192), float("nan"), dtype=torch.bfloat16, device="cuda")
+    _lib.check(lib.mmpfn_feature_attention_bf16(qkv.data_ptr(), att.data_ptr(), n_rows, T, _stream()), "feat_attn")
+    torch.cuda.synchronize()
+    x = qkv.float().view(n_rows, T, 3, 6, 32)
+    q, k, v = (x[:, :, j].permute(0, 2, 1, 3) for j in range(3))              # [rows, h, T, d]
+    ref = (torch.softmax(q @ k.transpose(-1, -2) / 32 ** 0.5, dim=-1) @ v).permute(0, 2, 1, 3).reshape(n_rows * T, 192)
+    assert not torch.isnan(att.float()).any()
+    assert (att.float() - ref).abs().max().item() < 0.03      # P and the output rounded to bf16, O(1) values
 
 
 def _one_layer_model(precision, seed=3):

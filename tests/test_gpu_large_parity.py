@@ -55,16 +55,19 @@ def test_ctx10k_vs_reference(precision):
             assert np.abs(k - ref[:, :, 0]).max() < 0.06 and np.abs(v - ref[:, :, 1]).max() < 0.06, (li,)
 
 
+@pytest.mark.parametrize("gain", ["g1", "g3"])
 @pytest.mark.parametrize("precision", ["bf16", "fp32"])
-def test_layer50k_vs_reference(precision):
+def test_layer50k_vs_reference(precision, gain):
     """The 50 000-key axis of configs[3]: ONE layer (feature attention, item attention with 50 000 train
     rows as keys, MLP) on a [50 128 rows, T = 3] state; 64 train rows and 64 test rows of the output against
-    the reference's own ``PerFeatureEncoderLayer`` modules.  The softmax is sharp here (qkv gain 3: scores
-    spread over tens of log2 units), so the running reference of the bf16 kernel moves and 1042 key tiles
-    accumulate."""
+    the reference's own ``PerFeatureEncoderLayer`` modules (1042 key tiles accumulate per query).
+    ``g1``: the reference's initialisation law.  ``g3``: scores nine times larger — a sharp softmax whose running
+    reference moves; there bf16 OPERANDS alone (q, k rounded to 8 bits: |score| ~ 30 -> +-0.1 in the exponent)
+    bound what any bf16 attention can reach, so bf16 is held to a loose bound and the kernel itself is checked
+    against same-operand arithmetic in ``test_item_attention_50k_keys_sharp``."""
     geom = cases.LAYER50K_GEOM
-    sd = make_state_dict(geom, seed=cases.LAYER50K_WSEED, qkv_gain=cases.LAYER50K_QKV_GAIN)
-    g = load_golden("large_layer50k")
+    sd = make_state_dict(geom, seed=cases.LAYER50K_WSEED, qkv_gain=cases.LAYER50K_GAINS[gain])
+    g = load_golden("large_layer50k_" + gain)
     n_tr, n_te, T = cases.LAYER50K_SHAPE
     model = B200PerFeatureTransformer(sd, geom, precision=precision, seed=0)
     state = torch.as_tensor(cases.layer_state(n_tr + n_te, T, seed=cases.LAYER50K_SSEED)).cuda()
@@ -78,10 +81,35 @@ def test_layer50k_vs_reference(precision):
     model.layers_test(te, te_b, kv, n_tr)
     out = torch.cat([tr[0], te[0]]).cpu().numpy()[cases.LAYER50K_ROWS]
     err = np.abs(out - g["out_rows"])
-    print(f"[layer50k {precision}] max|err| train rows {err[:64].max():.3e}, test rows {err[64:].max():.3e} "
-          f"(LayerNorm-ed values, |x| up to {np.abs(g['out_rows']).max():.1f})")
+    print(f"[layer50k {gain} {precision}] max|err| train rows {err[:64].max():.3e}, test rows {err[64:].max():.3e}, "
+          f"mean {err.mean():.2e} (LayerNorm-ed values, |x| up to {np.abs(g['out_rows']).max():.1f})")
     assert np.isfinite(out).all()
-    assert err.max() < (0.05 if bf else 2e-4), err.max()
+    tol = 2e-4 if not bf else (0.05 if gain == "g1" else 0.6)
+    assert err.max() < tol, err.max()
+
+
+def test_item_attention_50k_keys_sharp():
+    """The bf16 item-attention kernel over 50 000 keys with scores spread over +-60 log2 units (the running
+    reference moves, exponentials saturate against a stale reference and tiles are repeated), against fp32 torch
+    on the SAME bf16 operands: what is left is the kernel's own error (P rounded to bf16, polynomial 2^x)."""
+    lib = _lib.load()
+    B, T, n_q, n_kv, scale = 1, 1, 256, 50_000, 3.0
+    planes = B * T * 6
+    qpad, kpad = 256, (n_kv + 63) // 64 * 64
+    gen = torch.Generator().manual_seed(50)
+    q = (torch.randn(planes, qpad, 32, generator=gen) * scale).cuda().to(torch.bfloat16)
+    k = (torch.randn(planes, kpad, 32, generator=gen) * scale).cuda().to(torch.bfloat16)
+    vt = torch.randn(planes, 32, kpad, generator=gen).cuda().to(torch.bfloat16)
+    out = torch.full((B, n_q, T, 192), float("nan"), dtype=torch.bfloat16, device="cuda")
+    _lib.check(lib.mmpfn_item_attention_bf16(q.data_ptr(), k.data_ptr(), vt.data_ptr(), B, T, n_q, qpad, n_kv, kpad, 0,
+                                             out.data_ptr(), torch.cuda.current_stream().cuda_stream), "item_attention")
+    torch.cuda.synchronize()
+    err = 0.0
+    for h in range(6):
+        ref = torch.softmax(q[h, :n_q].float() @ k[h, :n_kv].float().T / 32 ** 0.5, dim=-1) @ vt[h, :, :n_kv].float().T
+        err = max(err, float((out[0, :, 0, h * 32:(h + 1) * 32].float() - ref).abs().max()))
+    print(f"[item attention, 50k keys, sharp] max|err| vs same-operand fp32: {err:.3e}")
+    assert err < 0.03, err
 
 
 @pytest.mark.parametrize("precision", ["bf16", "fp32"])

@@ -208,3 +208,29 @@ def test_multi_group_pass_equals_per_group(fit_mode):
     eng.multi_group = False
     b = eng.logits_staged(staged).clone()
     assert torch.isfinite(a).all() and torch.equal(a, b)
+
+
+def test_graph_replay_survives_scratch_growth():
+    """CUDA graphs hold raw pointers into the model's shared scratch buffers; a later, larger call replaces those
+    buffers.  Sizes 120 -> 360 -> 120 test rows through the graphed path must each equal the eager path, and the
+    graph cache stays bounded."""
+    from multimodalpfn_b200.classifier import MMPFNClassifier
+    from multimodalpfn_b200.preprocessing import transform_all
+    from multimodalpfn_b200.synth import Geometry, make_dataset, make_state_dict
+    geom = Geometry(mgm_heads=2, cap_heads=4)
+    sd = make_state_dict(geom, seed=3)
+    d = make_dataset("pad_ufes_small", 0)
+    clf = MMPFNClassifier(mixer_type="MGM+CAP", mgm_heads=2, cap_heads=4, features_per_group=2, n_estimators=4,
+                          model_path=(sd, geom), device="cuda", inference_precision="bf16",
+                          ignore_pretraining_limits=True, random_state=0)
+    clf.fit(d["X_train"], d["img_train"], d["y_train"])
+    eng = clf.executor_
+    X3 = np.concatenate([d["X_test"]] * 3)
+    I3 = np.concatenate([d["img_test"]] * 3)
+    for X, I in ((d["X_test"], d["img_test"]), (X3, I3), (d["X_test"], d["img_test"]), (X3[:77], I3[:77]),
+                 (X3[:200], I3[:200]), (X3[:33], I3[:33]), (d["X_test"], d["img_test"])):
+        staged = eng.stage(transform_all(clf.members_, X), I)
+        a = eng.logits_graphed(staged).clone()
+        b = eng.logits_staged(staged).clone()
+        assert torch.isfinite(a).all() and torch.equal(a, b), X.shape
+        assert len(eng._graphs) <= eng.max_graphs

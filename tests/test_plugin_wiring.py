@@ -52,8 +52,8 @@ def test_plugin_swaps_only_the_model(tmp_path, monkeypatch):
 
     # the patch only converts on CUDA devices; force the conversion for this CPU wiring test
     orig_convert = plugin.convert
-    monkeypatch.setattr(plugin, "convert", lambda m, *, device, precision, model_cls: orig_convert(
-        m, device=device, precision=precision, model_cls=model_cls))
+    monkeypatch.setattr(plugin, "convert", lambda m, *, device, precision, model_cls, pos_emb_device="cuda": orig_convert(
+        m, device=device, precision=precision, model_cls=model_cls, pos_emb_device=pos_emb_device))
     uninstall = plugin.install(precision="fp32", model_cls=Recorder)
     try:
         clf = C.MMPFNClassifier(**kw).fit(d["X_train"], d["img_train"], d["y_train"])
