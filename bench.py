@@ -18,8 +18,9 @@ like the reference does (inference.py:302-348), then the 300 test rows are class
   bounded sample of the same workload, scaled by the algorithmic FLOP ratio.
 
 With N>1 (torchrun, one rank per GPU) every rank classifies its own 300-row test chunk
-(weak scaling); the train context is built once per estimator on its owner rank and the K/V
-context is all-gathered over NCCL (multimodalpfn_b200/dist.py).
+(weak scaling); the train context is built once per estimator on its owner rank and the K/V context is
+all-gathered over NCCL layer by layer under the build (multimodalpfn_b200/dist.py); the probabilities of all ranks
+are all-gathered inside the timed step.  ``strong_scaling`` times a fixed total of 2400 test rows beside it.
 """
 from __future__ import annotations
 
@@ -362,8 +363,15 @@ def run_ours(args):
 
     use_graph = world == 1 and not args.no_graph
 
-    def step_device():
-        return eng.logits_graphed(staged) if use_graph else eng.logits_staged(staged)
+    gathered = {}
+
+    def step_device(st=None):
+        st = staged if st is None else st
+        lg = eng.logits_graphed(st) if use_graph else eng.logits_staged(st)
+        if world > 1:
+            # the tail on the device and the all-gather of every rank's probabilities belong to the step
+            gathered["p"] = eng.proba_gathered(lg, perms, n_classes=clf.n_classes_)
+        return lg
 
     flush = torch.empty(384 * 1024 * 1024, dtype=torch.uint8, device=dev)   # > 126 MB L2
 
@@ -400,6 +408,35 @@ def run_ours(args):
     value = world * n_te / (ms * 1e-3)
     proba_dev = proba_from_logits(lg, perms, n_classes=clf.n_classes_)
     assert np.allclose(proba_dev.sum(1), 1.0, atol=1e-5)
+    strong = None
+    if world > 1:
+        pg = gathered["p"]
+        assert pg.shape[0] == world * n_te
+        assert torch.allclose(pg[rank * n_te:(rank + 1) * n_te].cpu(), torch.as_tensor(proba_dev), atol=1e-5)
+        # strong scaling beside the weak line: a FIXED total of 2400 test rows split over the ranks
+        total_rows = 2400
+        per = total_rows // world
+        reps = (total_rows + n_te - 1) // n_te
+        Xs = np.concatenate([d["X_test"]] * reps)[rank * per:(rank + 1) * per]
+        Is = np.concatenate([d["img_test"]] * reps)[rank * per:(rank + 1) * per]
+        staged_s = eng.stage(transform_all(clf.members_, Xs), Is)
+        for _ in range(3):
+            step_device(staged_s)
+        sync_all()
+        evs2 = []
+        for _ in range(args.steps):
+            flush.zero_()
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record()
+            step_device(staged_s)
+            b.record()
+            evs2.append((a, b))
+        sync_all()
+        tms = torch.tensor([float(np.mean([a.elapsed_time(b) for a, b in evs2]))], device=dev)
+        dist.all_reduce(tms, op=dist.ReduceOp.MAX)
+        strong = {"value": per * world / (float(tms.item()) * 1e-3), "unit": "rows/s", "ms_per_step": float(tms.item()),
+                  "total_test_rows": per * world, "rows_per_rank": per, "scaling": "strong"}
+        staged = eng.stage(X_tests_host, img_test)
     if args.profile:
         if rank == 0:
             print(json.dumps({"profile_run": True, "ms_per_step": ms, "gpu_launches": int(launches)}), flush=True)
@@ -525,6 +562,8 @@ def run_ours(args):
         "kernels": extra,
         "cpu_baseline": cpu,
         "cached_context": cached,
+        "strong_scaling": strong,
+        "exchange": getattr(eng, "exchange", None),
         "wall_ms_per_step_incl_flush": t_wall * 1e3 / max(args.steps, 1),
         "peaks": peaks,
     }

@@ -176,6 +176,27 @@ int mmpfn_layers_test_multi(const mmpfn_geometry* g, const mmpfn_weights* w, flo
                             const mmpfn_segment* segs, int n_seg, int S, int n_train, void* const* kv, void* workspace,
                             size_t workspace_bytes, void* stream);
 
+/* The same passes over a RANGE of layers and with the K/V context addressed explicitly: what the multi-GPU
+ * engine (multimodalpfn_b200/dist.py) needs to all-gather layer l's K/V under layers l+1.. and to let the test
+ * pass read the gather buffer where the blocks land.  Per segment and layer the context block is
+ *     K0 [c][T][Np][32]  then  V0^T [c][T][32][Np]      (bf16, Np = n_train rounded up to 64)
+ * with c estimators back to back.  Train pass (train != 0): c = B, block of layer l written at
+ * kv + l * layer_stride.  Test pass: estimator b of the segment = (rank b / slots, slot b % slots) lives in the block at
+ * kv + l * layer_stride + rank * rank_stride with c = slots.  layer_stride 0 = blocks of consecutive layers are
+ * adjacent; slots 0 = all B estimators in one block (rank_stride unused): then this is mmpfn_layers_*_multi.
+ * Layers [layer_begin, layer_end) run; the state is carried in state_f32 / state_bf16 between calls. */
+typedef struct mmpfn_kv_segment {
+  int32_t B, T;
+  void* kv;
+  int64_t layer_stride;   /* bytes */
+  int32_t slots;
+  int32_t reserved;
+  int64_t rank_stride;    /* bytes */
+} mmpfn_kv_segment;
+int mmpfn_layers_run(const mmpfn_geometry* g, const mmpfn_weights* w, float* state_f32, uint16_t* state_bf16,
+                     const mmpfn_kv_segment* segs, int n_seg, int S, int n_train, int train, int layer_begin,
+                     int layer_end, void* workspace, size_t workspace_bytes, void* stream);
+
 /* ---- decoder + probability tail ------------------------------------------------------------ */
 /* transformer.py:392-396, :850-853: logits[b][s][:] = W2 gelu(W1 state[b][s][T-1] + b1) + b2.
  * state [B][S][T][E] -> logits [B][S][n_out]; hidden scratch [B*S][nhid] fp32. */

@@ -534,23 +534,31 @@ size_t mmpfn_layers_multi_ws_bytes(const mmpfn_geometry* g, const mmpfn_segment*
   return carve_multi(nullptr, segs, n_seg, S, M).bytes;
 }
 
-// train != 0: self-attention over the S rows, head-0 K/V written to kv[i] (may be NULL);
-// train == 0: the S rows are test rows attending to the n_train rows' context kv[i]
-static int layers_multi(const mmpfn_geometry* g, const mmpfn_weights* w, float* state, uint16_t* state_b,
-                        const mmpfn_segment* segs, int n_seg, int S, int n_train, int train, void* const* kv,
-                        void* workspace, size_t workspace_bytes, cudaStream_t st) {
+// One K/V context block per segment and layer: K0 [c][T][Np][32] then V0^T [c][T][32][Np] (bf16), c = the
+// estimators stored back to back (train pass: c = B; test pass: c = slots, see mmpfn_kv_segment).
+static size_t kv_block_elems(int c, int T, int n_pad) { return (size_t)2 * c * T * n_pad * kD; }
+
+// train != 0: self-attention over the S rows, head-0 K/V written to segs[i].kv (may be NULL);
+// train == 0: the S rows are test rows attending to the n_train rows' context segs[i].kv
+static int layers_run(const mmpfn_geometry* g, const mmpfn_weights* w, float* state, uint16_t* state_b,
+                      const mmpfn_kv_segment* ks, int n_seg, int S, int n_train, int train, int layer_begin,
+                      int layer_end, void* workspace, size_t workspace_bytes, cudaStream_t st) {
   MMPFN_TRY(check_geometry(g));
   MMPFN_TRY(require_device());
+  if (!ks || n_seg < 1 || n_seg > MMPFN_MAX_SEGMENTS) { set_error("layers_run: bad segment list"); return MMPFN_EINVAL; }
+  mmpfn_segment segs[MMPFN_MAX_SEGMENTS];
+  for (int i = 0; i < n_seg; ++i) { segs[i].B = ks[i].B; segs[i].T = ks[i].T; }
   long long M = 0;
   MMPFN_TRY(check_segments(segs, n_seg, S, &M));
-  if (!w || !w->layers_f32 || !w->layers_bf16 || !state || !state_b || !kv) { set_error("layers_multi: null argument (bf16 mode only)"); return MMPFN_EINVAL; }
-  if (!train) for (int i = 0; i < n_seg; ++i) if (!kv[i] || n_train < 1) { set_error("layers_multi: the test pass needs every segment's context"); return MMPFN_EINVAL; }
+  if (!w || !w->layers_f32 || !w->layers_bf16 || !state || !state_b) { set_error("layers_run: null argument (bf16 mode only)"); return MMPFN_EINVAL; }
+  if (layer_begin < 0 || layer_end > g->nlayers || layer_begin >= layer_end) { set_error("layers_run: bad layer range [%d, %d)", layer_begin, layer_end); return MMPFN_EINVAL; }
+  if (!train) for (int i = 0; i < n_seg; ++i) if (!ks[i].kv || n_train < 1) { set_error("layers_run: the test pass needs every segment's context"); return MMPFN_EINVAL; }
   MultiWs ws = carve_multi(workspace, segs, n_seg, S, M);
-  if (!workspace || workspace_bytes < ws.bytes) { set_error("layers_multi: workspace %zu < %zu bytes", workspace_bytes, ws.bytes); return MMPFN_EINVAL; }
+  if (!workspace || workspace_bytes < ws.bytes) { set_error("layers_run: workspace %zu < %zu bytes", workspace_bytes, ws.bytes); return MMPFN_EINVAL; }
   const int Sp = kv_pad(S), Np = kv_pad(n_train);
   LayerWs flat{};
   flat.hid_b = ws.hid_b; flat.qkv_b = ws.hid_b; flat.att_b = ws.att_b;
-  for (int l = 0; l < g->nlayers; ++l) {
+  for (int l = layer_begin; l < layer_end; ++l) {
     const LayerW lw = layer_w(w, l);
     // features: QKV over all tokens, attention per segment (rows of T_i tokens), out-projection + LN over all
     {
@@ -579,15 +587,20 @@ static int layers_multi(const mmpfn_geometry* g, const mmpfn_weights* w, float* 
         a.q = ws.seg[i].qi; a.out = ws.att_b + off * kE; a.B = B; a.T = T; a.n_q = S; a.Sq_pad = Sp;
         if (train) {
           q.k_out = ws.seg[i].ki; q.vt_out = ws.seg[i].vti;
-          if (kv[i]) {
-            uint16_t* kvl = (uint16_t*)kv[i] + (size_t)l * B * T * Sp * 2 * kD;
+          if (ks[i].kv) {
+            const size_t stride = ks[i].layer_stride > 0 ? (size_t)ks[i].layer_stride / 2 : kv_block_elems(B, T, Sp);
+            uint16_t* kvl = (uint16_t*)ks[i].kv + (size_t)l * stride;
             q.k0_out = kvl;
             q.vt0_out = kvl + (size_t)B * T * Sp * kD;
           }
           a.k = ws.seg[i].ki; a.vt = ws.seg[i].vti; a.n_kv = S; a.Skv_pad = Sp; a.shared_kv = 0;
         } else {
-          const uint16_t* kvl = (const uint16_t*)kv[i] + (size_t)l * B * T * Np * 2 * kD;
-          a.k = kvl; a.vt = kvl + (size_t)B * T * Np * kD; a.n_kv = n_train; a.Skv_pad = Np; a.shared_kv = 1;
+          const int c = ks[i].slots > 0 ? ks[i].slots : B;
+          const size_t stride = ks[i].layer_stride > 0 ? (size_t)ks[i].layer_stride / 2 : kv_block_elems(B, T, Np);
+          const uint16_t* kvl = (const uint16_t*)ks[i].kv + (size_t)l * stride;
+          a.k = kvl; a.vt = kvl + (size_t)c * T * Np * kD; a.n_kv = n_train; a.Skv_pad = Np; a.shared_kv = 1;
+          a.kv_slots = ks[i].slots > 0 ? ks[i].slots : 0;
+          a.kv_rank_stride = ks[i].rank_stride / 2;
         }
         MMPFN_TRY(proj_gemm(q, st));
         MMPFN_TRY(launch_tc_item_attn(a, st));
@@ -600,6 +613,18 @@ static int layers_multi(const mmpfn_geometry* g, const mmpfn_weights* w, float* 
   return MMPFN_OK;
 }
 
+static int layers_multi(const mmpfn_geometry* g, const mmpfn_weights* w, float* state, uint16_t* state_b,
+                        const mmpfn_segment* segs, int n_seg, int S, int n_train, int train, void* const* kv,
+                        void* workspace, size_t workspace_bytes, cudaStream_t st) {
+  if (!segs || !kv || n_seg < 1 || n_seg > MMPFN_MAX_SEGMENTS || !g) { set_error("layers_multi: bad segment list"); return MMPFN_EINVAL; }
+  mmpfn_kv_segment ks[MMPFN_MAX_SEGMENTS];
+  for (int i = 0; i < n_seg; ++i) {
+    ks[i].B = segs[i].B; ks[i].T = segs[i].T; ks[i].kv = kv[i]; ks[i].layer_stride = 0; ks[i].slots = 0; ks[i].reserved = 0;
+    ks[i].rank_stride = 0;
+  }
+  return layers_run(g, w, state, state_b, ks, n_seg, S, n_train, train, 0, g->nlayers, workspace, workspace_bytes, st);
+}
+
 int mmpfn_layers_train_multi(const mmpfn_geometry* g, const mmpfn_weights* w, float* state_f32, uint16_t* state_bf16,
                              const mmpfn_segment* segs, int n_seg, int S, void* const* kv, void* workspace,
                              size_t workspace_bytes, void* stream) {
@@ -610,6 +635,13 @@ int mmpfn_layers_test_multi(const mmpfn_geometry* g, const mmpfn_weights* w, flo
                             const mmpfn_segment* segs, int n_seg, int S, int n_train, void* const* kv, void* workspace,
                             size_t workspace_bytes, void* stream) {
   return layers_multi(g, w, state_f32, state_bf16, segs, n_seg, S, n_train, 0, kv, workspace, workspace_bytes, (cudaStream_t)stream);
+}
+
+int mmpfn_layers_run(const mmpfn_geometry* g, const mmpfn_weights* w, float* state_f32, uint16_t* state_bf16,
+                     const mmpfn_kv_segment* segs, int n_seg, int S, int n_train, int train, int layer_begin,
+                     int layer_end, void* workspace, size_t workspace_bytes, void* stream) {
+  return layers_run(g, w, state_f32, state_bf16, segs, n_seg, S, n_train, train, layer_begin, layer_end, workspace,
+                    workspace_bytes, (cudaStream_t)stream);
 }
 
 int mmpfn_decode(const mmpfn_geometry* g, const mmpfn_weights* w, const float* state, int B, int S, int T,

@@ -180,6 +180,11 @@ struct TcItemAttn {
   uint16_t* out;        // att, state layout [B][S][T][kE] bf16 (row (b,s,t), cols h*kD+d)
   int B, T, n_q, Sq_pad, n_kv, Skv_pad;
   int shared_kv;        // 1: kv planes are (b,t) (head 0 for all six q heads); 0: (b,t,h)
+  // shared_kv only: where estimator b's planes live.  kv_slots = 0: dense, plane (b,t) at (b*T + t) planes from k / vt.
+  // kv_slots = c > 0: the context sits in an all-gather buffer, c estimators back to back per rank chunk:
+  // estimator b = (rank b / c, slot b % c), its plane t at  rank * kv_rank_stride + (slot*T + t) planes  (elements).
+  int kv_slots;
+  long long kv_rank_stride;
 };
 int launch_tc_item_attn(const TcItemAttn& p, cudaStream_t st);
 

@@ -53,6 +53,7 @@ struct AttnArgs {
   uint16_t* out;
   int T, n_q, n_kv, shared_kv, q_tiles;
   int stack_rows;   // > 0: the six query heads of a (b, t) column are stacked on the tile's row axis, Sq_pad rows each
+  int kv_slots;     // shared_kv: estimators per rank chunk of the K/V context (>= 1; B when the context is dense)
 };
 
 #ifdef MMPFN_DEBUG
@@ -104,6 +105,13 @@ __device__ __forceinline__ void tma_load_3d_addr(uint32_t dst, const CUtensorMap
   asm volatile(
       "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
       ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1), "r"(c2)
+      : "memory");
+}
+__device__ __forceinline__ void tma_load_5d_addr(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1, int c2,
+                                                 int c3, int c4) {
+  asm volatile(
+      "cp.async.bulk.tensor.5d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6, %7}], [%2];"
+      ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4)
       : "memory");
 }
 __device__ __forceinline__ uint64_t sub_f32x2(uint64_t a, uint64_t b) {
@@ -228,7 +236,12 @@ __global__ void __launch_bounds__(A_THREADS, AttnCfg<BK>::kMinCtas)
   const int q0 = (blockIdx.x % p.q_tiles) * A_BQ;
   const int h = p.stack_rows ? 0 : plane % kH;
   const int bt = p.stack_rows ? plane : plane / kH;
-  const int kv_plane = p.shared_kv ? bt : plane;
+  // K / V^T planes through 5-D tensor maps {.., .., c2, c3, c4}: own planes (train pass) are (plane, 0, 0); the
+  // shared head-0 context (test pass) is (token column, slot, rank) — dense or inside an all-gather buffer
+  const int kb = bt / p.T;
+  const int kc2 = p.shared_kv ? bt - kb * p.T : plane;
+  const int kc3 = p.shared_kv ? kb % p.kv_slots : 0;
+  const int kc4 = p.shared_kv ? kb / p.kv_slots : 0;
   const int nkt = (p.n_kv + BK - 1) / BK;
 
   if (threadIdx.x == 0) {
@@ -254,8 +267,8 @@ __global__ void __launch_bounds__(A_THREADS, AttnCfg<BK>::kMinCtas)
     if (elect_one()) {
       mbar_expect_tx_addr(q_full, A_Q_BYTES + (nkt > 1 ? 2 : 1) * C::kKTx);
       tma_load_3d_addr(sbase, &map_q, q_full, 0, q0, plane);
-      tma_load_3d_addr(sbase + C::kOffK, &map_k, q_full, 0, 0, kv_plane);
-      if (nkt > 1) tma_load_3d_addr(sbase + C::kOffK + C::kKSlot, &map_k, q_full, 0, BK, kv_plane);
+      tma_load_5d_addr(sbase + C::kOffK, &map_k, q_full, 0, 0, kc2, kc3, kc4);
+      if (nkt > 1) tma_load_5d_addr(sbase + C::kOffK + C::kKSlot, &map_k, q_full, 0, BK, kc2, kc3, kc4);
       // refill g: V^T(g) and K(g+2) into slot g & 1 once done[g & 1] has completed g/2 + 1 times
       for (int g = 0; g < nkt; ++g) {
         const uint32_t s = g & 1;
@@ -264,9 +277,9 @@ __global__ void __launch_bounds__(A_THREADS, AttnCfg<BK>::kMinCtas)
         mbar_expect_tx_addr(kv_full + s * 8, C::kVtBytes + (has_k ? C::kKTx : 0));
 #pragma unroll
         for (int kb = 0; kb < C::kNKB; ++kb)
-          tma_load_3d_addr(sbase + C::kOffVt + s * C::kVtBytes + kb * (kD * 128), &map_vt, kv_full + s * 8,
-                           g * BK + kb * 64, 0, kv_plane);
-        if (has_k) tma_load_3d_addr(sbase + C::kOffK + s * C::kKSlot, &map_k, kv_full + s * 8, 0, (g + 2) * BK, kv_plane);
+          tma_load_5d_addr(sbase + C::kOffVt + s * C::kVtBytes + kb * (kD * 128), &map_vt, kv_full + s * 8,
+                           g * BK + kb * 64, 0, kc2, kc3, kc4);
+        if (has_k) tma_load_5d_addr(sbase + C::kOffK + s * C::kKSlot, &map_k, kv_full + s * 8, 0, (g + 2) * BK, kc2, kc3, kc4);
       }
     }
   } else if (warp == 5) {
@@ -518,19 +531,32 @@ int launch_tc_item_attn(const TcItemAttn& p, cudaStream_t st) {
     const cuuint32_t box[3] = {kD, A_BQ, 1};
     MMPFN_TRY(encode_map(&mq, p.q, 3, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_64B));
   }
-  {
-    const cuuint64_t dims[3] = {(cuuint64_t)kD, (cuuint64_t)p.n_kv, (cuuint64_t)planes_kv};
-    const cuuint64_t strides[2] = {(cuuint64_t)kD * 2, (cuuint64_t)p.Skv_pad * kD * 2};
-    const cuuint32_t box[3] = {kD, BK, 1};
-    MMPFN_TRY(encode_map(&mk, p.k, 3, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_64B));
+  // K / V^T: {.., .., c2, c3, c4} = (plane, 0, 0) for own planes; (token column, slot, rank) for the shared context
+  int slots = 1;
+  cuuint64_t n2 = (cuuint64_t)planes_kv, n3 = 1, n4 = 1;
+  const cuuint64_t plane_bytes = (cuuint64_t)p.Skv_pad * kD * 2;
+  cuuint64_t s3 = plane_bytes * n2, s4 = plane_bytes * n2;
+  if (p.shared_kv) {
+    slots = p.kv_slots > 0 ? p.kv_slots : p.B;
+    if (p.B % slots != 0) { set_error("item attention: %d estimators do not fill chunks of %d", p.B, slots); return MMPFN_EINVAL; }
+    n2 = (cuuint64_t)p.T; n3 = (cuuint64_t)slots; n4 = (cuuint64_t)(p.B / slots);
+    s3 = plane_bytes * p.T;
+    s4 = p.kv_slots > 0 ? (cuuint64_t)p.kv_rank_stride * 2 : s3 * slots;
+    if (s4 % 16 != 0 || (n4 > 1 && s4 < s3 * slots)) { set_error("item attention: bad rank stride of the K/V context"); return MMPFN_EINVAL; }
   }
   {
-    const cuuint64_t dims[3] = {(cuuint64_t)p.n_kv, (cuuint64_t)kD, (cuuint64_t)planes_kv};
-    const cuuint64_t strides[2] = {(cuuint64_t)p.Skv_pad * 2, (cuuint64_t)p.Skv_pad * kD * 2};
-    const cuuint32_t box[3] = {64, kD, 1};
-    MMPFN_TRY(encode_map(&mvt, p.vt, 3, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_128B));
+    const cuuint64_t dims[5] = {(cuuint64_t)kD, (cuuint64_t)p.n_kv, n2, n3, n4};
+    const cuuint64_t strides[4] = {(cuuint64_t)kD * 2, plane_bytes, s3, s4};
+    const cuuint32_t box[5] = {kD, BK, 1, 1, 1};
+    MMPFN_TRY(encode_map(&mk, p.k, 5, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_64B));
   }
-  AttnArgs a{p.out, p.T, p.n_q, p.n_kv, p.shared_kv, q_tiles, stack ? p.Sq_pad : 0};
+  {
+    const cuuint64_t dims[5] = {(cuuint64_t)p.n_kv, (cuuint64_t)kD, n2, n3, n4};
+    const cuuint64_t strides[4] = {(cuuint64_t)p.Skv_pad * 2, plane_bytes, s3, s4};
+    const cuuint32_t box[5] = {64, kD, 1, 1, 1};
+    MMPFN_TRY(encode_map(&mvt, p.vt, 5, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_128B));
+  }
+  AttnArgs a{p.out, p.T, p.n_q, p.n_kv, p.shared_kv, q_tiles, stack ? p.Sq_pad : 0, slots};
   const dim3 grid((unsigned)(grid_planes * q_tiles));
 #ifdef MMPFN_DEBUG
   // tuning builds only (-DMMPFN_DEBUG): MMPFN_ATTN_PP = polynomial pairs of every 24.  The product

@@ -21,13 +21,14 @@ import torch
 from . import _lib
 from .model import B200PerFeatureTransformer, TrainContext
 
-__all__ = ["proba_from_logits", "B200InferenceEngine"]
+__all__ = ["proba_device", "proba_from_logits", "B200InferenceEngine"]
 
 
-def proba_from_logits(logits: torch.Tensor, class_perms: Sequence[Optional[np.ndarray]], *, n_classes: int,
-                      class_counts=None, softmax_temperature: float = 0.9, average_before_softmax: bool = False,
-                      balance_probabilities: bool = False) -> np.ndarray:
-    """classifier.py:544-576 on the device: logits [n_est, Nte, n_out] -> float32 [Nte, n_classes].
+def proba_device(logits: torch.Tensor, class_perms: Sequence[Optional[np.ndarray]], *, n_classes: int,
+                 class_counts=None, softmax_temperature: float = 0.9, average_before_softmax: bool = False,
+                 balance_probabilities: bool = False) -> torch.Tensor:
+    """classifier.py:544-566 on the device: logits [n_est, Nte, n_out] -> float32 [Nte, n_classes] (device tensor,
+    not yet renormalised on the host).
 
     Quirk mirrored from the reference: the ``[:, :n_classes]`` slice lives inside
     ``if softmax_temperature != 1`` (classifier.py:544-547); with temperature 1 and no class
@@ -52,7 +53,12 @@ def proba_from_logits(logits: torch.Tensor, class_perms: Sequence[Optional[np.nd
     _lib.check(lib.mmpfn_proba_tail(logits.data_ptr(), perm_d.data_ptr(), None if prior_d is None else prior_d.data_ptr(),
                                     n_est, S, n_out, width, float(softmax_temperature), int(average_before_softmax),
                                     proba.data_ptr(), torch.cuda.current_stream(dev).cuda_stream), "mmpfn_proba_tail")
-    out = proba.cpu().numpy()
+    return proba
+
+
+def proba_from_logits(logits: torch.Tensor, class_perms: Sequence[Optional[np.ndarray]], **kw) -> np.ndarray:
+    """``proba_device`` + the D2H copy + the host renormalisation of classifier.py:568-576 -> float32 numpy."""
+    out = proba_device(logits, class_perms, **kw).cpu().numpy()
     return out / out.sum(axis=1, keepdims=True)      # classifier.py:576 (after the D2H copy, like the reference)
 
 

@@ -1,10 +1,10 @@
-"""torchrun --nproc-per-node N tools/check_dist.py — sharded engine (context broadcast over NCCL)
-vs the unsharded engine on every rank's own test chunk."""
+"""torchrun --nproc-per-node N tools/check_dist.py — sharded engine (per-layer K/V all-gather over NCCL, test pass
+reading the gather buffer in place) vs the unsharded engine on every rank's own test chunk: bit-identical logits."""
 import os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np, torch, torch.distributed as dist
 from multimodalpfn_b200.classifier import MMPFNClassifier
-from multimodalpfn_b200.dist import ShardedEngine, all_gather_rows
+from multimodalpfn_b200.dist import ShardedEngine
 from multimodalpfn_b200.engine import proba_from_logits
 from multimodalpfn_b200.synth import Geometry, make_dataset, make_state_dict
 
@@ -17,19 +17,23 @@ d = make_dataset("pad_ufes_small", 0)
 rng = np.random.default_rng(5 + rank)
 Xte = d["X_test"][rng.permutation(len(d["X_test"]))]
 img = rng.standard_normal(d["img_test"].shape).astype(np.float32)
-for precision in ("fp32", "bf16"):
+for precision in ("bf16", "fp32"):
     clf = MMPFNClassifier(mixer_type="MGM+CAP", mgm_heads=2, cap_heads=4, n_estimators=8, model_path=(sd, geom),
                           device=f"cuda:{local}", inference_precision=precision, ignore_pretraining_limits=True,
                           random_state=0).fit(d["X_train"], d["img_train"], d["y_train"])
     X_tests = [m.transform(Xte) for m in clf.members_]
     ref = clf.executor_.logits(X_tests, img, graph=False).clone()
     sh = ShardedEngine(clf.executor_, rank, world)
-    got = sh.logits(X_tests, img)
+    got = sh.logits(X_tests, img).clone()
+    got2 = sh.logits(X_tests, img)                    # second call: the gather buffer is reused
     err = (got - ref).abs().max().item()
-    p = torch.as_tensor(proba_from_logits(got, [m.class_perm for m in clf.members_], n_classes=clf.n_classes_)).cuda()
-    allp = all_gather_rows(p)
-    ok = allp.shape[0] == world * p.shape[0] and torch.equal(allp[rank * p.shape[0]:(rank + 1) * p.shape[0]], p)
-    print(f"rank {rank}/{world} {precision}: max |sharded - unsharded| logits = {err:.3e}; gather ok = {ok}", flush=True)
-    assert err < (1e-4 if precision == "fp32" else 5e-2) and ok
+    perms = [m.class_perm for m in clf.members_]
+    p = torch.as_tensor(proba_from_logits(got, perms, n_classes=clf.n_classes_)).cuda()
+    allp = sh.proba_gathered(got, perms, n_classes=clf.n_classes_)
+    ok = allp.shape[0] == world * p.shape[0] and torch.allclose(allp[rank * p.shape[0]:(rank + 1) * p.shape[0]], p, atol=1e-6)
+    print(f"rank {rank}/{world} {precision} mode={sh.plan.mode}: max |sharded - unsharded| logits = {err:.3e}; "
+          f"repeat equal = {bool(torch.equal(got, got2))}; gather ok = {bool(ok)}; exchange = {sh.exchange}", flush=True)
+    assert err == 0.0 if sh.plan.mode != "broadcast" and precision == "bf16" else err < 1e-4, err
+    assert ok and torch.equal(got, got2)
 dist.barrier()
 dist.destroy_process_group()

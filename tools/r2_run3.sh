@@ -6,7 +6,7 @@ timeout -k 5 120 python tools/attn_bench.py >> $L 2>&1
 timeout -k 5 120 python tools/attn_bench.py 300 2000 1 >> $L 2>&1
 timeout -k 5 120 python tools/attn_bench.py 10000 10000 0 1.0 1 42 >> $L 2>&1
 timeout -k 5 120 python tools/attn_trace.py >> $L 2>&1
-timeout -k 5 1500 python -m pytest tests -m gpu -q -s -p no:cacheprovider -x > gpurun_out/r2_s3_pytest.log 2>&1
+timeout -k 5 1500 python -m pytest tests -m gpu -q -s -p no:cacheprovider > gpurun_out/r2_s3_pytest.log 2>&1
 echo "pytest rc=$?" >> $L; tail -3 gpurun_out/r2_s3_pytest.log >> $L
 timeout -k 5 600 python tools/ref_probe.py > gpurun_out/r2_ref_probe.jsonl 2> gpurun_out/r2_ref_probe.err
 echo "probe rc=$?" >> $L
