@@ -290,6 +290,8 @@ def plugin_e2e(args, dev_index, flush, precision):
     D2H of the probabilities."""
     import torch
     from multimodalpfn_b200 import plugin
+    from oracle import ref_compat
+    ref_compat.install()
     uninstall = plugin.install(precision=precision, pos_emb_device="cuda", mode="engine")
     try:
         clf, d = _reference_classifier(f"cuda:{dev_index}", N_EST)

@@ -349,18 +349,10 @@ __global__ void __launch_bounds__(A_THREADS, AttnCfg<BK>::kMinCtas)
       if (!next_ready) mbar_wait_lean(done + sb * 8, (j >> 1) & 1);
       tc_fence_after();
       if (threadIdx.x == 0) ATTN_TRACE(j * 8 + 1);
-      // S(j) starts its way into the registers; under its latency the hand-off of the PREVIOUS tile is
-      // finished: P(j-1) is in TMEM (wait::st) -> one arrival per warp on p_full
-      tmem_ld_cols<BK>(tmem_s, sv);
-      if (j > 0) {
-        tmem_st_wait();
-        tc_fence_before();
-        __syncwarp();
-        if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(p_full + (sb ^ 1) * 8) : "memory");
-      }
+
       // the whole row of S into registers (masking the keys a partial last tile does not have)
-      auto load_row = [&](bool issue) {
-        if (issue) tmem_ld_cols<BK>(tmem_s, sv);
+      auto load_row = [&]() {
+        tmem_ld_cols<BK>(tmem_s, sv);
         tmem_ld_wait();
         if (valid < BK) {
 #pragma unroll
@@ -419,7 +411,7 @@ __global__ void __launch_bounds__(A_THREADS, AttnCfg<BK>::kMinCtas)
         }
         return fmaxf(fmaxf(mx0, mx1), fmaxf(mx2, mx3));
       };
-      load_row(false);
+      load_row();
       if (threadIdx.x == 0) ATTN_TRACE(j * 8 + 2);
       if (j == 0) m_ref = row_max();             // first tile: the reference is the true maximum of the tile
       // Later tiles: exponentials are taken against the reference of the earlier tiles, and no maximum
@@ -436,7 +428,7 @@ __global__ void __launch_bounds__(A_THREADS, AttnCfg<BK>::kMinCtas)
       const bool any_moved = __any_sync(0xffffffffu, moved);   // tcgen05.ld is warp-collective
       float alpha = 1.0f;
       if (any_moved) {
-        load_row(true);
+        load_row();
         if (moved) {
           const float mx = fmaxf(row_max(), m_ref);
           alpha = fast_exp2((m_ref - mx) * c);
@@ -459,15 +451,17 @@ __global__ void __launch_bounds__(A_THREADS, AttnCfg<BK>::kMinCtas)
         for (int i = 0; i < 32; ++i) o[i] = __float_as_uint(__uint_as_float(o[i]) * alpha);
         tmem_st32(tmem_o + lane_off, o);
       }
+      // hand-off: P(j) (and a rescaled O) are in TMEM -> one arrival per warp on p_full.  (Deferring this under the
+      // next tile's TMEM load was measured: 446 instead of 471 TFLOP/s — the MMA thread starts P V(j) later.)
+      tmem_st_wait();
       if (threadIdx.x == 0) ATTN_TRACE(j * 8 + 5);
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(p_full + sb * 8) : "memory");
+      if (threadIdx.x == 0) ATTN_TRACE(j * 8 + 6);
       next_ready = __all_sync(0xffffffffu, probe);
       if (threadIdx.x == 0) ATTN_TRACE(j * 8 + 7);
     }
-    // hand-off of the last tile
-    tmem_st_wait();
-    tc_fence_before();
-    __syncwarp();
-    if (lane == 0) asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(p_full + ((nkt - 1) & 1) * 8) : "memory");
     uint32_t v[32];
     // the last iteration of the MMA thread: tcgen05 ops complete in order, so this covers all P V
     mbar_wait_lean(done + ((nkt - 1) & 1) * 8, (((nkt - 1) >> 1) + 1) & 1);

@@ -132,14 +132,18 @@ class B200InferenceEngine:
             self._pinned_bufs[key] = buf
         return buf
 
-    def stage(self, X_test_per_member: Sequence[Optional[np.ndarray]], image_test: Optional[np.ndarray]):
+    def stage(self, X_test_per_member: Sequence[Optional[np.ndarray]], image_test: Optional[np.ndarray], *,
+              image_dev: Optional[torch.Tensor] = None):
         """Host -> device copies of one call's inputs (the per-step H2D traffic): the preprocessed test
-        table of every estimator and the test embeddings, through pinned host buffers."""
+        table of every estimator and the test embeddings, through pinned host buffers.  ``image_dev``: the test
+        embeddings already on the device (several engines of one call share one upload)."""
         dev = self.model.device
         if self._stage_event is not None:
             self._stage_event.synchronize()        # the previous call's DMA has left the pinned buffers
         img_test_dev = None
-        if image_test is not None and self.img_train_dev is not None:        # inference.py:311-316
+        if image_dev is not None and self.img_train_dev is not None:
+            img_test_dev = image_dev
+        elif image_test is not None and self.img_train_dev is not None:        # inference.py:311-316
             img = np.asarray(image_test, dtype=np.float32)
             if img.ndim == 2:
                 img = img[:, None]
@@ -265,7 +269,7 @@ class B200InferenceEngine:
         return out
 
     def logits(self, X_test_per_member: Sequence[Optional[np.ndarray]], image_test: Optional[np.ndarray], *,
-               graph: bool = True) -> torch.Tensor:
-        staged = self.stage(X_test_per_member, image_test)
+               graph: bool = True, image_dev: Optional[torch.Tensor] = None) -> torch.Tensor:
+        staged = self.stage(X_test_per_member, image_test, image_dev=image_dev)
         out = self.logits_graphed(staged) if graph else self.logits_staged(staged)
         return out

@@ -63,14 +63,19 @@ class B200PluginEngine:
     built FROM the engine the reference prepared: its fitted per-estimator preprocessors, preprocessed
     train tables, permuted labels, ensemble configs and train embeddings are taken as they are, so the
     tensors that reach the model are the reference's.  What changes is how ``iter_outputs``
-    (``inference.py:282-351``) produces its logits: instead of a serial loop of B = 1 forwards it transforms
-    the test table with every estimator's own preprocessor (the reference's code), then runs ALL estimators
-    as one batched CUDA pass (``engine.B200InferenceEngine``) and yields ``(logits[Nte, n_out], config)``
-    per estimator in the reference's order — the rest of ``predict_proba`` (``classifier.py:532-576``) is
-    untouched."""
+    (``inference.py:282-351``) produces its logits: instead of a serial loop of B = 1 forwards that each wait
+    for their host transform, the estimators run as a few batched CUDA passes (``engine.B200InferenceEngine``,
+    one CUDA graph each) and the passes are PIPELINED with the host work — while the GPU runs the pass of one
+    sub-batch, the host already transforms the test table for the next one with that estimator's own
+    preprocessor (the reference's numpy/sklearn code, ~2-5 ms per estimator, GIL-bound).  ``(logits[Nte,
+    n_out], config)`` is yielded per estimator in the reference's order — the rest of ``predict_proba``
+    (``classifier.py:532-576``) is untouched.
+
+    Sub-batches: estimators sharing a preprocessed width, ``stage_size`` at a time, cheapest recipe first (so
+    that the GPU starts early)."""
 
     def __init__(self, ref_engine, *, device, precision="bf16", pos_emb_device="cuda", model_cls=None,
-                 cache_context=False):
+                 cache_context=False, stage_size=2):
         import numpy as np
         from .engine import B200InferenceEngine
         self.ref = ref_engine
@@ -78,18 +83,50 @@ class B200PluginEngine:
         self.ensemble_configs = ref_engine.ensemble_configs
         self.model = convert(ref_engine.model, device=device, precision=precision, model_cls=model_cls,
                              pos_emb_device=pos_emb_device)
-        members = [dict(X_train=None if Xt is None else np.asarray(Xt, dtype=np.float32),
-                        y_train=np.asarray(yt, dtype=np.float32), class_perm=None)
-                   for Xt, yt in zip(ref_engine.X_trains, ref_engine.y_trains)]
-        self.engine = B200InferenceEngine(self.model, members, ref_engine.image_train, cache_context=cache_context)
+        self.members = [dict(X_train=None if Xt is None else np.asarray(Xt, dtype=np.float32),
+                             y_train=np.asarray(yt, dtype=np.float32), class_perm=None)
+                        for Xt, yt in zip(ref_engine.X_trains, ref_engine.y_trains)]
+        by_width = {}
+        for i, m in enumerate(self.members):
+            by_width.setdefault(-1 if m["X_train"] is None else m["X_train"].shape[1], []).append(i)
+        self.stages = []
+        for _, idx in sorted(by_width.items()):                     # fewer columns = the cheaper recipe first
+            for a in range(0, len(idx), max(1, stage_size)):
+                sub = idx[a:a + max(1, stage_size)]
+                eng = B200InferenceEngine(self.model, [self.members[i] for i in sub], ref_engine.image_train,
+                                          cache_context=cache_context)
+                if self.stages:                                     # the train-row image tokens are the same for all
+                    eng._img_tok_train = self.stages[0][1].train_image_tokens()
+                self.stages.append((sub, eng))
+        self._img_pin = None
+
+    def _upload_image(self, image_test):
+        import numpy as np
+        import torch
+        if image_test is None or self.ref.image_train is None:
+            return None
+        img = np.asarray(image_test, dtype=np.float32)
+        if img.ndim == 2:
+            img = img[:, None]
+        if self._img_pin is None or tuple(self._img_pin.shape) != img.shape:
+            self._img_pin = torch.empty(img.shape, dtype=torch.float32, pin_memory=self.model.device.type == "cuda")
+        # (the previous call ended with a host sync — the NaN-flag read — so its DMA has left this buffer)
+        self._img_pin.numpy()[...] = img
+        return self._img_pin.to(self.model.device, non_blocking=True)
 
     def iter_outputs(self, X, image_test, *, device=None, autocast=None):
         import numpy as np
-        X_tests = [None if X is None or m["X_train"] is None else np.asarray(pre.transform(X).X, dtype=np.float32)
-                   for pre, m in zip(self.preprocessors, self.engine.members)]            # inference.py:303
-        logits = self.engine.logits(X_tests, image_test)
-        self.engine.check_nan()                                                             # transformer.py:790-796
-        for lg, cfg in zip(logits, self.ensemble_configs):
+        image_dev = self._upload_image(image_test)
+        outs = [None] * len(self.members)
+        for sub, eng in self.stages:
+            X_tests = [None if X is None or self.members[i]["X_train"] is None
+                       else np.asarray(self.preprocessors[i].transform(X).X, dtype=np.float32) for i in sub]   # inference.py:303
+            lg = eng.logits(X_tests, None, image_dev=image_dev)       # asynchronous: H2D + one CUDA-graph replay
+            for k, i in enumerate(sub):
+                outs[i] = lg[k]
+        for _, eng in self.stages:
+            eng.check_nan()                                           # transformer.py:790-796 (first host sync of the call)
+        for lg, cfg in zip(outs, self.ensemble_configs):
             yield lg, cfg
 
 

@@ -37,7 +37,6 @@ print("softmax thread 0 per tile: deltas [wait done, S in regs, sweep, P st issu
 tot = []
 for j in range(nkt):
     s = buf[j * 8:j * 8 + 8].copy()
-    s[6] = s[5]            # (the hand-off now happens at the top of the next tile, under its TMEM load)
     nxt = buf[(j + 1) * 8] if j + 1 < nkt else s[7]
     d = [int(s[i + 1] - s[i]) for i in range(7)]
     tot.append(int(nxt - s[0]))
@@ -47,4 +46,4 @@ print("median tile", int(np.median(tot[2:-2])), "cycles")
 print("mma thread per tile: [P ready at, issue+commit took] and lag from softmax arrive to P-ready")
 for j in list(range(8)) + [nkt - 2, nkt - 1]:
     a, b = buf[4096 + j * 2], buf[4096 + j * 2 + 1]
-    print(j, int(a - t0), int(b - a), "lag from next loop top", int(a - buf[(j + 1) * 8]) if j + 1 < nkt else None)
+    print(j, int(a - t0), int(b - a), "lag from the softmax arrive", int(a - buf[j * 8 + 6]))
