@@ -25,6 +25,13 @@ NVCC_FLAGS = [
     "--expt-relaxed-constexpr", "-Xcompiler", "-fPIC", "-shared", "-cudart", "static",
     "-Xptxas", "-v",
 ] + (["-DMMPFN_DEBUG"] if DEBUG else [])
+# tuning only: extra -D flags and a library name suffix for A/B builds (MMPFN_VARIANT="name:-DATTN_PIN=1 ...")
+_VARIANT = os.environ.get("MMPFN_VARIANT", "")
+if _VARIANT:
+    _vname, _, _vflags = _VARIANT.partition(":")
+    NVCC_FLAGS = NVCC_FLAGS + _vflags.split()
+    LIB = os.path.join(HERE, f"libmmpfn_b200_{_vname}.so")
+    STAMP = os.path.join(HERE, f".libmmpfn_b200_{_vname}.stamp")
 
 
 def _nvcc() -> str:

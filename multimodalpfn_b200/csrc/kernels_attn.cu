@@ -31,7 +31,29 @@ namespace {
 constexpr int A_BQ = 128;
 constexpr int A_Q_BYTES = A_BQ * kD * 2;          // 8 KB  (64B rows, 64B swizzle)
 constexpr int A_THREADS = 192;
-constexpr int kPolyPairsDefault = 6;              // of 24 pairs per tile (measured optimum)
+#ifndef ATTN_PP
+#define ATTN_PP 7
+#endif
+constexpr int kPolyPairsDefault = ATTN_PP;        // of 24 pairs per tile (measured optimum)
+#ifndef ATTN_KAHEAD
+#define ATTN_KAHEAD 4
+#endif
+#ifndef ATTN_KBEHIND
+#define ATTN_KBEHIND 5
+#endif
+#ifndef ATTN_PROBE_AT
+#define ATTN_PROBE_AT 1000                        // pair step of the sweep at which the next tile's S is probed (>= NP: after it)
+#endif
+#ifndef ATTN_PIN
+#define ATTN_PIN 1
+#endif
+// a value the compiler must keep in a register instead of recomputing it from special registers at every use
+__device__ __forceinline__ uint32_t pin_u32(uint32_t v) {
+#if ATTN_PIN
+  asm volatile("mov.u32 %0, %0;" : "+r"(v));
+#endif
+  return v;
+}
 
 template <int BK>
 struct AttnCfg {
@@ -223,12 +245,12 @@ __global__ void __launch_bounds__(A_THREADS, AttnCfg<BK>::kMinCtas)
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
   uint64_t* bars = (uint64_t*)(smem + C::kOffBar);
-  const uint32_t sbase = smem_u32(smem);
-  const uint32_t bar0 = sbase + C::kOffBar;
+  const uint32_t sbase = pin_u32(smem_u32(smem));
+  const uint32_t bar0 = pin_u32(sbase + C::kOffBar);
   const uint32_t q_full = bar0, kv_full = bar0 + 8, p_full = bar0 + 24, done = bar0 + 40;   // [2] each after q_full
   uint32_t* tmem_slot = (uint32_t*)(bars + 8);
 
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int warp = threadIdx.x >> 5, lane = (int)pin_u32(threadIdx.x & 31);
   // Train pass: plane = (b*T + t)*kH + h, q tiles of a plane are adjacent CTAs.  Test pass (all six query
   // heads read the head-0 K/V of their column, multi_head_attention.py:436-445): the heads are stacked on
   // the row axis — row = h * Sq_pad + s of column bt — so that 6 x 300 rows fill 15 tiles instead of 18.
@@ -325,7 +347,7 @@ __global__ void __launch_bounds__(A_THREADS, AttnCfg<BK>::kMinCtas)
   } else {
     // ---- softmax warps: thread = one query row ----
     const int r = warp * 32 + lane;
-    const uint32_t lane_off = (uint32_t)(warp * 32) << 16;
+    const uint32_t lane_off = pin_u32((uint32_t)(warp * 32) << 16);
     const float c = 0.17677669529663687f * 1.4426950408889634f;   // log2(e)/sqrt(d)
     // m_ref is the score the exponent of this row is measured from.  It only follows the running
     // maximum when that has grown by more than kTau (log2 units): p = 2^((s - m_ref) c) then stays
@@ -334,8 +356,8 @@ __global__ void __launch_bounds__(A_THREADS, AttnCfg<BK>::kMinCtas)
     constexpr float kSumLimit = 256.0f;          // 2^kTau, kTau = 8
     constexpr float kMasked = -1.0e30f;          // a key past n_kv: 2^x of it is 0 (MUFU) or 2^-100 (polynomial), V^T is 0 there
     constexpr int kNP = BK / 2;                  // pairs of keys per row and tile
-    constexpr int kAhead = 4;                    // pairs whose scaled argument is ready ahead of their ex2
-    constexpr int kBehind = 5;                   // pairs whose ex2 is in flight before the first consumer reads one
+    constexpr int kAhead = ATTN_KAHEAD;          // pairs whose scaled argument is ready ahead of their ex2
+    constexpr int kBehind = ATTN_KBEHIND;        // pairs whose ex2 is in flight before the first consumer reads one
     float m_ref = -INFINITY, l_run = 0.f;
     bool next_ready = false;
     uint32_t sv[BK];
@@ -365,7 +387,9 @@ __global__ void __launch_bounds__(A_THREADS, AttnCfg<BK>::kMinCtas)
       // (row sum FADD2, bf16 pack F2FP, in place: slot k of sv then holds the packed pair).  Values are
       // transformed in place: s -> x -> p.  No row maximum is tracked here.
       const uint64_t c2 = pack_f32x2(c, c);
-      auto sweep = [&](float mc) -> float {
+      bool probe = false;
+      const uint32_t probe_bar = done + (sb ^ 1) * 8, probe_par = ((j + 1) >> 1) & 1;
+      auto sweep = [&](float mc, bool with_probe) -> float {
         const uint64_t nmc2 = pack_f32x2(-mc, -mc);
         uint64_t lsum2 = 0ull;                                // (0.f, 0.f)
         auto scale = [&](int k) {
@@ -394,6 +418,8 @@ __global__ void __launch_bounds__(A_THREADS, AttnCfg<BK>::kMinCtas)
           if (k + kAhead < kNP) scale(k + kAhead);
           if (k < kNP) expo(k);
           if (k >= kBehind) retire(k - kBehind);
+          // the probe's ~200-cycle round trip runs under the rest of the sweep
+          if (k == ATTN_PROBE_AT && with_probe) probe = j + 1 < nkt && mbar_test_addr(probe_bar, probe_par);
         }
         float lsum0, lsum1;
         unpack_f32x2(lsum2, lsum0, lsum1);
@@ -420,9 +446,9 @@ __global__ void __launch_bounds__(A_THREADS, AttnCfg<BK>::kMinCtas)
       // running maximum of n keys moves ~ log n times, and a sum that merely crowds the limit just
       // refreshes the reference — is the true maximum taken and the sweep repeated.  S was consumed in
       // place, so the repeat reads it from TMEM again: P only overwrites the S columns after the decision.
-      float lsum = sweep(m_ref * c);
+      float lsum = sweep(m_ref * c, true);
       // early probe of the next tile's S: consumed at the top of the next iteration
-      const bool probe = j + 1 < nkt && mbar_test_addr(done + (sb ^ 1) * 8, ((j + 1) >> 1) & 1);
+      if (ATTN_PROBE_AT >= kNP + kBehind) probe = j + 1 < nkt && mbar_test_addr(probe_bar, probe_par);
       if (threadIdx.x == 0) ATTN_TRACE(j * 8 + 3);
       const bool moved = !(lsum <= kSumLimit);
       const bool any_moved = __any_sync(0xffffffffu, moved);   // tcgen05.ld is warp-collective
@@ -434,7 +460,7 @@ __global__ void __launch_bounds__(A_THREADS, AttnCfg<BK>::kMinCtas)
           alpha = fast_exp2((m_ref - mx) * c);
           m_ref = mx;
         }
-        lsum = sweep(m_ref * c);
+        lsum = sweep(m_ref * c, false);
       }
       tmem_st_cols<BK / 2>(tmem_s, sv);          // P(j) over the first half of the S(j) columns
       l_run = l_run * alpha + lsum;
