@@ -130,7 +130,8 @@ int mmpfn_stem_image(const mmpfn_geometry* g, const mmpfn_weights* w, const floa
  *           = one set shared by the B estimators of a task (inference.py:272), S*H_img*E = one per entry
  *           (independent tasks packed on the batch axis)
  *   y       [B][.]: S labels per estimator, y_bstride apart (NaN = unlabeled test row)
- *   y_mean  [B], y_present_mask [B] (bit c set iff class c occurs among the train labels)
+ *   y_mean  [B], y_present_mask [B] (bit c set iff class c occurs among the train labels, c <= 62; bit 63 set =
+ *   regression checkpoint: no class-rank step, the target value itself is embedded, model/loading.py:387-388)
  *   pos_emb [T-1][E]
  *   state_f32 [B][S][T][E] out; state_bf16 same shape, may be NULL.
  * nan_flag (int32, device): set to 1 if any produced value is NaN (transformer.py:727-731, :790-796). */

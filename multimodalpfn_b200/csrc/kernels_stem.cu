@@ -230,9 +230,13 @@ __global__ void __launch_bounds__(kE) stem_tokens_kernel(
     const float ind = isnan(yy) ? -2.0f : 0.0f;
     if (isnan(yy)) yy = y_mean[b];
     const uint64_t mask = y_mask[b];
-    int rank = 0;
-    for (int c = 0; c < 64; ++c) rank += (((mask >> c) & 1ull) && ((float)c < yy)) ? 1 : 0;
-    emit(T - 1, fmaf((float)rank, yenc_w[e * 2], fmaf(ind, yenc_w[e * 2 + 1], yenc_b[e])));
+    float val = yy;                       // regression checkpoints (bit 63): the target value itself, no rank step
+    if (!(mask >> 63)) {
+      int rank = 0;
+      for (int c = 0; c < 63; ++c) rank += (((mask >> c) & 1ull) && ((float)c < yy)) ? 1 : 0;
+      val = (float)rank;
+    }
+    emit(T - 1, fmaf(val, yenc_w[e * 2], fmaf(ind, yenc_w[e * 2 + 1], yenc_b[e])));
   }
   if (bad) atomicOr(nan_flag, 1);
 }

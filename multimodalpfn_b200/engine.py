@@ -93,7 +93,7 @@ class B200InferenceEngine:
                                              for i in idx])).to(dev)
             # label statistics need a host sync (unique labels): once here, not per call
             self.groups.append(dict(F=F, idx=idx, X_train=Xtr, y_train=ytr, ctx=None,
-                                    label_stats=type(model).label_stats(ytr)))
+                                    label_stats=model.label_stats(ytr)))
         self.img_train_dev = None if self.image_train is None else torch.from_numpy(self.image_train).to(dev)
         self._img_tok_train = None
         self.nan_flag = torch.zeros(1, dtype=torch.int32, device=dev)

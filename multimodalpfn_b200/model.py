@@ -49,6 +49,7 @@ class TrainContext:
     y_mask: torch.Tensor                  # [B] uint64 as int64
     pos_emb: torch.Tensor                 # [T-1, E]
     precision: int
+    train_out: Optional[torch.Tensor] = None   # [B, Ntr, E]: y-token of the train rows after the last layer (on request)
 
 
 class B200PerFeatureTransformer:
@@ -74,6 +75,8 @@ class B200PerFeatureTransformer:
             self.w = PackedWeights(state_dict, geom, self.device, with_bf16=True)
         self._g = C.byref(self.w.c_geom)
         self._w = C.byref(self.w.c_weights)
+        self._w_test = C.byref(self.w.c_weights_test)      # second query set of two_sets_of_queries checkpoints
+        self._cached_ctx = None                            # the reference's model-level train-set cache
         self._pos_cache = {}
         self._buf = {}
         # bumped whenever a shared scratch buffer is replaced (and its old storage freed): CUDA graphs captured
@@ -167,10 +170,16 @@ class B200PerFeatureTransformer:
                                                self._stream()), "mmpfn_stem_tab_fit")
         return stats
 
-    @staticmethod
-    def label_stats(y_train: torch.Tensor):
-        """y_train [B, Ntr] (class ids as floats) -> (mean [B], presence bitmask [B]).
-        encoders.py:461 (nanmean for the test-row fill) and :954-958 (unique train labels)."""
+    REGRESSION_MASK = -(1 << 63)        # bit 63 of the presence mask: "embed the target value itself"
+
+    def label_stats(self, y_train: torch.Tensor):
+        """y_train [B, Ntr] -> (mean [B], presence bitmask [B]).
+        Classification (class ids as floats): encoders.py:461 (nanmean for the test-row fill) and :954-958 (unique
+        train labels, for the ordinal rank).  Regression checkpoints: the mean only — no rank step exists
+        (model/loading.py:387-388) and bit 63 of the mask tells the stem kernel so."""
+        if getattr(self.w, "regression", False):
+            mask = torch.full((y_train.shape[0],), self.REGRESSION_MASK, dtype=torch.int64, device=y_train.device)
+            return y_train.to(torch.float32).mean(dim=1).contiguous(), mask
         yl = y_train.to(torch.int64)
         if not torch.equal(yl.to(y_train.dtype), y_train) or int(yl.min()) < 0 or int(yl.max()) > 62:
             raise ValueError("labels must be integer class ids in [0, 62]")
@@ -220,7 +229,7 @@ class B200PerFeatureTransformer:
         B, S, T, _ = state.shape
         nbytes = self.lib.mmpfn_layers_ws_bytes(self._g, B, S, T, self.precision)
         ws = self._scratch("layers", nbytes)
-        _lib.check(self.lib.mmpfn_layers_test(self._g, self._w, state.data_ptr(), _ptr(state_b), B, S, T, n_train,
+        _lib.check(self.lib.mmpfn_layers_test(self._g, self._w_test, state.data_ptr(), _ptr(state_b), B, S, T, n_train,
                                               self.precision, kv.data_ptr(), ws.data_ptr(), nbytes, self._stream()),
                    "mmpfn_layers_test")
 
@@ -237,7 +246,7 @@ class B200PerFeatureTransformer:
                                                          kvp, ws.data_ptr(), nbytes, self._stream()),
                        "mmpfn_layers_train_multi")
         else:
-            _lib.check(self.lib.mmpfn_layers_test_multi(self._g, self._w, state.data_ptr(), state_b.data_ptr(), arr, n, S,
+            _lib.check(self.lib.mmpfn_layers_test_multi(self._g, self._w_test, state.data_ptr(), state_b.data_ptr(), arr, n, S,
                                                         n_train, kvp, ws.data_ptr(), nbytes, self._stream()),
                        "mmpfn_layers_test_multi")
 
@@ -253,7 +262,8 @@ class B200PerFeatureTransformer:
         plain = (_lib.Segment * n)(*[_lib.Segment(int(s["B"]), int(s["T"])) for s in segs])
         nbytes = self.lib.mmpfn_layers_multi_ws_bytes(self._g, plain, n, S)
         ws = self._scratch("layers", nbytes)
-        _lib.check(self.lib.mmpfn_layers_run(self._g, self._w, state.data_ptr(), state_b.data_ptr(), arr, n, S,
+        _lib.check(self.lib.mmpfn_layers_run(self._g, self._w if n_train is None else self._w_test, state.data_ptr(),
+                                             state_b.data_ptr(), arr, n, S,
                                              0 if n_train is None else int(n_train), 1 if n_train is None else 0,
                                              int(layer_begin), int(layer_end), ws.data_ptr(), nbytes, self._stream()),
                    "mmpfn_layers_run")
@@ -313,7 +323,7 @@ class B200PerFeatureTransformer:
                              "or use a NaN-handling encoder (an all-NaN column or inf in a train column).")
 
     def fit_context(self, X_train, img_train, y_train, *, X_all=None, img_tok_train=None, check=True,
-                    label_stats=None, nan_flag=None) -> TrainContext:
+                    label_stats=None, nan_flag=None, keep_train_out=False) -> TrainContext:
         """Run the train rows through the stem and the 12 layers once; keep the K/V context.
 
         X_train [B, Ntr, F] (or [Ntr, F]) / img_train [Ntr, n_tok, img_dim] / y_train [B, Ntr].
@@ -354,11 +364,13 @@ class B200PerFeatureTransformer:
             if check:
                 self._check_nan(flag)
             return TrainContext(B=B, n_train=n_train, F=F, T=T, n_tok=n_tok, kv=kv, tab_stats=stats, y_mean=y_mean,
-                                y_mask=y_mask, pos_emb=pos, precision=self.precision)
+                                y_mask=y_mask, pos_emb=pos, precision=self.precision,
+                                train_out=state[:, :, T - 1].clone() if keep_train_out else None)
 
     def predict_with_context(self, ctx: TrainContext, X_test, img_test, *, img_tok_test=None, check=True,
-                             nan_flag=None):
-        """Test rows only -> logits [B, Nte, n_out]."""
+                             nan_flag=None, return_embeddings=False):
+        """Test rows only -> logits [B, Nte, n_out] (with ``return_embeddings``: also the y-token of the test
+        rows after the last layer, [B, Nte, E] — the reference's ``test_embeddings``, transformer.py:862-866)."""
         with torch.cuda.device(self.device):
             X_test, img_test = self._prep(X_test, img_test)
             if img_tok_test is None and img_test is not None:
@@ -377,6 +389,8 @@ class B200PerFeatureTransformer:
             logits = self.decode(state)
             if check:
                 self._check_nan(flag)
+            if return_embeddings:
+                return logits, state[:, :, ctx.T - 1].clone()
             return logits
 
     # ---- several estimator groups at once (bf16): one launch per flat sublayer for all of them ----------
@@ -445,7 +459,7 @@ class B200PerFeatureTransformer:
             self._layers_multi(st, stb, [(c.B, c.T) for c in ctxs], n_test, [c.kv for c in ctxs], ctxs[0].n_train)
             return [self.decode(v[0]) for v in views]
 
-    def forward_batch(self, X_full, img_full, y_train, *, check=True):
+    def forward_batch(self, X_full, img_full, y_train, *, check=True, return_embeddings=False):
         """Reference-equivalent joint forward for B estimators sharing the image embeddings:
         X_full [B, S, F] (train rows first), img_full [S, n_tok, img_dim], y_train [B, Ntr]
         -> logits [B, Nte, n_out].  Identical to ``_forward`` (transformer.py:555-867) because train
@@ -467,35 +481,82 @@ class B200PerFeatureTransformer:
             flag = torch.zeros(1, dtype=torch.int32, device=self.device)
             ctx = self.fit_context(X_tr, None, y_train, X_all=X_full,
                                    img_tok_train=None if img_tok is None else img_tok[:n_train].contiguous(),
-                                   check=False, nan_flag=flag)
+                                   check=False, nan_flag=flag, keep_train_out=return_embeddings)
             if img_full is not None:
                 ctx.n_tok = img_full.shape[1]
-            return self.predict_with_context(ctx, X_te, None,
-                                             img_tok_test=None if img_tok is None else img_tok[n_train:].contiguous(),
-                                             check=check, nan_flag=flag)
+            out = self.predict_with_context(ctx, X_te, None,
+                                            img_tok_test=None if img_tok is None else img_tok[n_train:].contiguous(),
+                                            check=check, nan_flag=flag, return_embeddings=return_embeddings)
+            if return_embeddings:
+                return out[0], ctx.train_out, out[1]
+            return out
+
+    def empty_trainset_representation_cache(self):
+        """transformer.py:999-1001"""
+        self._cached_ctx = None
 
     def __call__(self, *args, only_return_standard_out: bool = True, categorical_inds=None,
                  single_eval_pos: Optional[int] = None, **kwargs):
         """The reference's 4-positional-argument inference call (transformer.py:540-543):
-        ``model(style, x [S,1,F], image [S,n_tok,768], y [Ntr]) -> [Nte, 1, n_out]``."""
+        ``model(style, x [S,1,F], image [S,n_tok,768], y [Ntr]) -> [Nte, 1, n_out]``.
+
+        With ``cache_trainset_representation`` set (the reference's model-level cache,
+        multi_head_attention.py:328-336, layer.py:305-309): a call with ``y`` and ``single_eval_pos`` builds and
+        KEEPS the train context (rows past ``single_eval_pos``, if any, are classified against it); a call with
+        ``y=None, single_eval_pos=None`` classifies its rows against the kept context.
+        ``only_return_standard_out=False`` returns the reference's dictionary (transformer.py:855-867):
+        ``standard`` plus ``train_embeddings`` / ``test_embeddings`` (the y-token after the last layer)."""
         if kwargs:
             raise AssertionError(f"unsupported keyword arguments: {sorted(kwargs)}")        # transformer.py:515-516
         if len(args) != 4:
             raise ValueError("Unrecognized input. Please follow the doc string.")          # transformer.py:545
         style, x, image, y = args
         assert style is None                                                               # transformer.py:592
-        if not only_return_standard_out:
-            raise NotImplementedError("only the standard decoder output is produced")
-        if y is None or not single_eval_pos:
-            raise NotImplementedError("use fit_context()/predict_with_context() for the cached-context form")
         if x is not None:
             if x.dim() != 3 or x.shape[1] != 1:
                 raise ValueError("x must be [S, 1, F] (the engine passes batch size 1, inference.py:305)")
             x = x[:, 0]
         if image is not None and image.dim() > 3:
             image = torch.movedim(image, 0, 1)[0]                                           # transformer.py:586-588
+        want_emb = not only_return_standard_out
+
+        def pack(logits, train_emb, test_emb):
+            std = logits[0][:, None, :]
+            if not want_emb:
+                return std
+            return {"standard": std, "train_embeddings": train_emb[0][:, None, :], "test_embeddings": test_emb[0][:, None, :]}
+
+        if self.cache_trainset_representation and not single_eval_pos:                      # transformer.py:593-595
+            assert y is None
+            if self._cached_ctx is None:
+                raise AssertionError("the train-set representation cache is empty")         # layer.py:307
+            out = self.predict_with_context(self._cached_ctx, None if x is None else x[None], image,
+                                            return_embeddings=want_emb)
+            if want_emb:
+                empty = out[1].new_zeros((1, 0, out[1].shape[-1]))
+                return pack(out[0], empty, out[1])
+            return pack(out, None, None)
+        assert y is not None and single_eval_pos                                            # transformer.py:597-598
         y = y.reshape(-1)
         if y.shape[0] != single_eval_pos:
             raise AssertionError("For main y, y must not be given for target time steps")   # transformer.py:695-698
-        logits = self.forward_batch(None if x is None else x[None], image, y[None])
-        return logits[0][:, None, :]
+        n_train = int(single_eval_pos)
+        S = x.shape[0] if x is not None else image.shape[0]
+        if self.cache_trainset_representation:
+            # the cached form: the stem statistics come from the rows of THIS call (encoders.py:368-371)
+            with torch.cuda.device(self.device):
+                Xd, imgd = self._prep(None if x is None else x[None], image)
+                ctx = self.fit_context(None if Xd is None else Xd[:, :n_train].contiguous(),
+                                       None if imgd is None else imgd[:n_train].contiguous(), y[None], X_all=Xd,
+                                       keep_train_out=want_emb)
+                self._cached_ctx = ctx
+                if S > n_train:
+                    out = self.predict_with_context(ctx, None if Xd is None else Xd[:, n_train:].contiguous(),
+                                                    None if imgd is None else imgd[n_train:].contiguous(),
+                                                    return_embeddings=want_emb)
+                    return pack(out[0], ctx.train_out, out[1]) if want_emb else pack(out, None, None)
+                empty_l = torch.zeros((1, 0, self.geom.n_out), dtype=torch.float32, device=self.device)
+                empty_e = torch.zeros((1, 0, self.geom.emsize), dtype=torch.float32, device=self.device)
+                return pack(empty_l, ctx.train_out, empty_e)
+        out = self.forward_batch(None if x is None else x[None], image, y[None], return_embeddings=want_emb)
+        return pack(*out) if want_emb else pack(out, None, None)

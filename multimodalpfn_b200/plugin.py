@@ -131,33 +131,41 @@ class B200PluginEngine:
 
 
 def install(precision: str = "bf16", model_cls=None, pos_emb_device: str = "cuda", mode: str = "engine"):
-    """Patch ``mmpfn.models.mmpfn.classifier.create_inference_engine``; returns an ``uninstall()``.
+    """Patch ``create_inference_engine`` where the reference's estimators look it up
+    (``mmpfn.models.mmpfn.classifier`` and ``.regressor``: ``MMPFNRegressor`` runs the same forward with a
+    bar-distribution head, regressor.py:577-730); returns an ``uninstall()``.
 
     ``mode="model"``: the reference's engine keeps its serial per-estimator loop and only its ``.model`` is
     swapped (one B = 1 CUDA forward per estimator).  ``mode="engine"`` (default): the engine object itself is
     replaced by ``B200PluginEngine`` (all estimators in one batched pass) — what SURVEY.md section 7 step 1(i)
     describes.  Both leave every line of the reference's ``fit`` / ``predict_proba`` in charge."""
     import mmpfn.models.mmpfn.classifier as C
+    import mmpfn.models.mmpfn.regressor as R
 
     orig = C.create_inference_engine
     if getattr(orig, "_mmpfn_b200", False):
         return lambda: None
+    orig_r = R.create_inference_engine
 
-    @functools.wraps(orig)
-    def create_inference_engine(**kw):
-        engine = orig(**kw)
-        dev = kw["device_"]
-        if getattr(dev, "type", str(dev)) == "cuda" and hasattr(engine, "model"):
-            if mode == "engine" and hasattr(engine, "preprocessors") and hasattr(engine, "X_trains"):
-                return B200PluginEngine(engine, device=dev, precision=precision, pos_emb_device=pos_emb_device,
-                                        model_cls=model_cls)
-            engine.model = convert(engine.model, device=dev, precision=precision, model_cls=model_cls,
-                                   pos_emb_device=pos_emb_device)
-        return engine
+    def wrap(fn):
+        @functools.wraps(fn)
+        def create_inference_engine(**kw):
+            engine = fn(**kw)
+            dev = kw["device_"]
+            if getattr(dev, "type", str(dev)) == "cuda" and hasattr(engine, "model"):
+                if mode == "engine" and hasattr(engine, "preprocessors") and hasattr(engine, "X_trains"):
+                    return B200PluginEngine(engine, device=dev, precision=precision, pos_emb_device=pos_emb_device,
+                                            model_cls=model_cls)
+                engine.model = convert(engine.model, device=dev, precision=precision, model_cls=model_cls,
+                                       pos_emb_device=pos_emb_device)
+            return engine
+        create_inference_engine._mmpfn_b200 = True
+        return create_inference_engine
 
-    create_inference_engine._mmpfn_b200 = True
-    C.create_inference_engine = create_inference_engine
+    C.create_inference_engine = wrap(orig)
+    R.create_inference_engine = wrap(orig_r)
 
     def uninstall():
         C.create_inference_engine = orig
+        R.create_inference_engine = orig_r
     return uninstall

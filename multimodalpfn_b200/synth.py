@@ -56,7 +56,8 @@ def _normal(rng, shape, std, mean=0.0):
 
 
 def make_state_dict(geom: Geometry = Geometry(), seed: int = 1, *, residual_std: float = 0.05,
-                    qkv_gain: float = 1.0, decoder_gain: float = 1.0) -> dict[str, np.ndarray]:
+                    qkv_gain: float = 1.0, decoder_gain: float = 1.0,
+                    two_sets_of_queries: bool = False, regression: bool = False) -> dict[str, np.ndarray]:
     """Random weights under the reference's state_dict names (numpy float32).
 
     ``residual_std`` scales ``_w_out`` / ``linear2`` (0.05 = SURVEY.md section 8(d) weights,
@@ -104,13 +105,28 @@ def make_state_dict(geom: Geometry = Geometry(), seed: int = 1, *, residual_std:
         sd["moe.gate.bias"] = _uniform(rng, (geom.mgm_heads,), 1 / math.sqrt(I))
     fpg = geom.features_per_group
     sd["encoder.5.layer.weight"] = _uniform(rng, (E, 2 * fpg), 1 / math.sqrt(2 * fpg))
-    sd["y_encoder.2.layer.weight"] = _uniform(rng, (E, 2), 1 / math.sqrt(2))
-    sd["y_encoder.2.layer.bias"] = _uniform(rng, (E,), 1 / math.sqrt(2))
+    # the regression y-encoder has no class-rank step (model/loading.py:374-398: NaN handling, Linear), so its
+    # Linear is step 1 instead of 2; the checkpoint also carries the bar-distribution borders of the criterion
+    ykey = "y_encoder.1.layer." if regression else "y_encoder.2.layer."
+    sd[ykey + "weight"] = _uniform(rng, (E, 2), 1 / math.sqrt(2))
+    sd[ykey + "bias"] = _uniform(rng, (E,), 1 / math.sqrt(2))
+    if regression:
+        # borders of geom.n_out buckets over a standardised target: normal quantiles (regressor.py:390-540 rescales them)
+        qs = np.linspace(0.0, 1.0, geom.n_out + 1)[1:-1]
+        from statistics import NormalDist
+        inner = np.array([NormalDist().inv_cdf(float(q)) for q in qs])
+        sd["criterion.borders"] = np.concatenate([[inner[0] - 1.0], inner, [inner[-1] + 1.0]]).astype(np.float32)
+        sd["criterion.losses_per_bucket"] = np.zeros(geom.n_out, dtype=np.float32)      # bar_distribution.py:460-461
     a_qkv = math.sqrt(3.0) * math.sqrt(2.0 / (H * D + E)) * qkv_gain
     for l in range(geom.nlayers):
         p = f"transformer_encoder.layers.{l}."
         for att in ("self_attn_between_features", "self_attn_between_items"):
-            sd[p + att + "._w_qkv"] = _uniform(rng, (3, H, D, E), a_qkv)
+            if two_sets_of_queries and att == "self_attn_between_items":
+                # multi_head_attention.py:216-260: a second query set for the test rows replaces the fused tensor
+                sd[p + att + "._w_q"] = _uniform(rng, (2, H, D, E), a_qkv)
+                sd[p + att + "._w_kv"] = _uniform(rng, (2, H, D, E), a_qkv)
+            else:
+                sd[p + att + "._w_qkv"] = _uniform(rng, (3, H, D, E), a_qkv)
             sd[p + att + "._w_out"] = _normal(rng, (H, D, E), residual_std)
         sd[p + "mlp.linear1.weight"] = _uniform(rng, (Hid, E), 1 / math.sqrt(E))
         sd[p + "mlp.linear2.weight"] = _normal(rng, (E, Hid), residual_std)
@@ -123,15 +139,17 @@ def make_state_dict(geom: Geometry = Geometry(), seed: int = 1, *, residual_std:
     return sd
 
 
-def make_checkpoint_config(geom: Geometry = Geometry()) -> dict:
+def make_checkpoint_config(geom: Geometry = Geometry(), *, two_sets_of_queries: bool = False,
+                           regression: bool = False) -> dict:
     """The minimal ``config`` dict the reference's loader accepts (SURVEY.md Appendix B;
     reference ``model/loading.py:253-305``, ``model/config.py:18-108``)."""
     return dict(
         adaptive_max_seq_len_to_max_full_table_size=150000, batch_size=4, emsize=geom.emsize,
-        features_per_group=geom.features_per_group, max_num_classes=geom.n_out, nhead=geom.nhead,
-        remove_duplicate_features=False, seq_len=4000, task_type="multiclass", num_buckets=1000,
+        features_per_group=geom.features_per_group, max_num_classes=0 if regression else geom.n_out, nhead=geom.nhead,
+        remove_duplicate_features=False, seq_len=4000, task_type="regression" if regression else "multiclass",
+        num_buckets=geom.n_out if regression else 1000,
         max_num_features=85, aggregate_k_gradients=1, nlayers=geom.nlayers,
-        nhid_factor=geom.nhid_factor,
+        nhid_factor=geom.nhid_factor, **({"two_sets_of_queries": True} if two_sets_of_queries else {}),
     )
 
 

@@ -42,30 +42,53 @@ class PackedWeights:
         self.geom = geom
         self.device = torch.device(device)
         E, H, D, Hid, L = geom.emsize, geom.nhead, geom.d_k, geom.nhid, geom.nlayers
-        if any(k.endswith("._w_q") or k.endswith("._w_kv") for k in sd):
-            raise NotImplementedError("checkpoints with two_sets_of_queries (_w_q/_w_kv) are not supported yet")
-        blocks = []
-        for l in range(L):
-            p = f"transformer_encoder.layers.{l}."
-            for att in ("self_attn_between_features", "self_attn_between_items"):
-                wqkv = sd[p + att + "._w_qkv"]
-                assert wqkv.shape == (3, H, D, E), wqkv.shape
-                blocks.append(wqkv.reshape(3 * H * D, E))
-                blocks.append(sd[p + att + "._w_out"].reshape(H * D, E).T)       # [e][h*D+d]
-            blocks.append(sd[p + "mlp.linear1.weight"])
-            blocks.append(sd[p + "mlp.linear2.weight"])
-        layers = np.concatenate([np.ascontiguousarray(b).reshape(-1) for b in blocks]).astype(np.float32)
+        # Checkpoints with ``two_sets_of_queries`` (multi_head_attention.py:216-260) carry, for the item attention,
+        # ``_w_q [2,H,D,E]`` + ``_w_kv [2,H,D,E]`` instead of ``_w_qkv [3,H,D,E]``: query set 0 serves the train rows
+        # and set 1 the test rows (layer.py:357, ``use_second_set_of_queries``).  The train pass and the test pass are
+        # separate launches here, so the second set simply is the test pass's copy of the layer block.
+        def qkv_of(prefix, q_set):
+            if prefix + "._w_qkv" in sd:
+                w = sd[prefix + "._w_qkv"]
+            else:
+                wq, wkv = sd[prefix + "._w_q"], sd[prefix + "._w_kv"]
+                assert wq.shape[1:] == (H, D, E) and wkv.shape == (2, H, D, E), (wq.shape, wkv.shape)
+                w = np.stack([wq[min(q_set, wq.shape[0] - 1)], wkv[0], wkv[1]])
+            assert w.shape == (3, H, D, E), w.shape
+            return w.reshape(3 * H * D, E)
+
+        self.two_sets_of_queries = any(k.endswith("self_attn_between_items._w_q") and v.shape[0] == 2 for k, v in sd.items())
+
+        def layer_blocks(q_set):
+            blocks = []
+            for l in range(L):
+                p = f"transformer_encoder.layers.{l}."
+                for att in ("self_attn_between_features", "self_attn_between_items"):
+                    blocks.append(qkv_of(p + att, q_set if att == "self_attn_between_items" else 0))
+                    blocks.append(sd[p + att + "._w_out"].reshape(H * D, E).T)       # [e][h*D+d]
+                blocks.append(sd[p + "mlp.linear1.weight"])
+                blocks.append(sd[p + "mlp.linear2.weight"])
+            return np.concatenate([np.ascontiguousarray(b).reshape(-1) for b in blocks]).astype(np.float32)
+
+        layers = layer_blocks(0)
         self._t = {}
         self._t["layers_f32"] = torch.from_numpy(layers).to(self.device)
         if with_bf16:
             self._t["layers_bf16"] = self._t["layers_f32"].to(torch.bfloat16)
+        if self.two_sets_of_queries:
+            self._t["layers_test_f32"] = torch.from_numpy(layer_blocks(1)).to(self.device)
+            if with_bf16:
+                self._t["layers_test_bf16"] = self._t["layers_test_f32"].to(torch.bfloat16)
 
         def put(name, arr):
             self._t[name] = torch.from_numpy(np.ascontiguousarray(arr, dtype=np.float32)).to(self.device)
 
         put("enc_w", sd["encoder.5.layer.weight"])
-        put("yenc_w", sd["y_encoder.2.layer.weight"])
-        put("yenc_b", sd["y_encoder.2.layer.bias"])
+        # regression checkpoints (max_num_classes = 0): the y-encoder has no class-rank step, its Linear is step 1
+        # (model/loading.py:374-398); the target value itself is embedded
+        self.regression = "y_encoder.2.layer.weight" not in sd
+        ykey = "y_encoder.1.layer." if self.regression else "y_encoder.2.layer."
+        put("yenc_w", sd[ykey + "weight"])
+        put("yenc_b", sd[ykey + "bias"])
         put("dec_w1", sd["decoder_dict.standard.0.weight"])
         put("dec_b1", sd["decoder_dict.standard.0.bias"])
         put("dec_w2", sd["decoder_dict.standard.2.weight"])
@@ -136,6 +159,13 @@ class PackedWeights:
         for name in _lib.WEIGHT_FIELDS:
             t = self._t.get(name)
             setattr(self.c_weights, name, None if t is None else t.data_ptr())
+        # the weights the TEST pass uses: the same struct unless the checkpoint has a second set of item queries
+        self.c_weights_test = self.c_weights
+        if self.two_sets_of_queries:
+            self.c_weights_test = _lib.Weights()
+            for name in _lib.WEIGHT_FIELDS:
+                t = self._t.get({"layers_f32": "layers_test_f32", "layers_bf16": "layers_test_bf16"}.get(name, name))
+                setattr(self.c_weights_test, name, None if t is None else t.data_ptr())
         expected = _lib.load().mmpfn_layer_weight_elems(C.byref(self.c_geom)) * L
         if expected != layers.size:
             raise RuntimeError(f"layer weight block mismatch: packed {layers.size}, library expects {expected}")
@@ -144,7 +174,7 @@ class PackedWeights:
         return self._t[name]
 
     def n_params(self) -> int:
-        return sum(t.numel() for k, t in self._t.items() if k != "layers_bf16")
+        return sum(t.numel() for k, t in self._t.items() if not k.endswith("_bf16"))
 
 
 def geometry_from_checkpoint(config: dict, state_dict, *, mixer_type, mgm_heads, cap_heads,
@@ -164,7 +194,7 @@ def load_checkpoint(path, *, mixer_type="MGM+CAP", mgm_heads=8, cap_heads=8, fea
     """Read the reference checkpoint format ``{"state_dict", "config"}`` (``model/loading.py:427-444``)."""
     ckpt = torch.load(path, map_location="cpu", weights_only=False)
     sd = ckpt["state_dict"]
-    sd = {k: v for k, v in sd.items() if not k.startswith("criterion.")}
+    sd = {k: v for k, v in sd.items() if not k.startswith("criterion.")}      # bar-distribution borders: host side
     geom = geometry_from_checkpoint(ckpt.get("config", {}), sd, mixer_type=mixer_type, mgm_heads=mgm_heads,
                                     cap_heads=cap_heads, features_per_group=features_per_group)
     return sd, geom

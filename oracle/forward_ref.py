@@ -128,12 +128,20 @@ def group_features(X, fpg):
 # ---------------------------------------------------------------------------------------------
 # y stem (a3) — model/loading.py:374-398, encoders.py:453-493, :949-974
 # ---------------------------------------------------------------------------------------------
-def stem_y(y_train, n_rows, w_y, b_y):
+def y_encoder_weights(sd):
+    """(weight, bias, regression): the classification y-encoder is NaN handling -> class rank -> Linear (step 2),
+    the regression one has no rank step, so its Linear is step 1 (model/loading.py:374-398)."""
+    if "y_encoder.2.layer.weight" in sd:
+        return sd["y_encoder.2.layer.weight"], sd["y_encoder.2.layer.bias"], False
+    return sd["y_encoder.1.layer.weight"], sd["y_encoder.1.layer.bias"], True
+
+
+def stem_y(y_train, n_rows, w_y, b_y, regression=False):
     """[Ntr] labels -> [n_rows, E]; rows past Ntr are the NaN-padded test rows
     (transformer.py:682-718)."""
     n_tr = y_train.shape[0]
     yy = torch.cat([y_train.to(torch.float32), torch.full((n_rows - n_tr,), float("nan"))])
-    return stem_y_apply(yy, stem_y_fit(y_train), w_y, b_y)
+    return stem_y_apply(yy, stem_y_fit(y_train), w_y, b_y, regression)
 
 
 def stem_y_fit(y_train):
@@ -141,11 +149,12 @@ def stem_y_fit(y_train):
     return dict(mean=torch.nanmean(y_train), uniq=torch.unique(y_train))
 
 
-def stem_y_apply(yy, st, w_y, b_y):
+def stem_y_apply(yy, st, w_y, b_y, regression=False):
     ind = torch.isnan(yy) * -2.0
     yy = torch.where(torch.isnan(yy), st["mean"], yy)
-    rank = (yy[:, None] > st["uniq"][None]).sum(-1).to(torch.float32)   # encoders.py:961-964
-    return torch.stack([rank, ind.to(torch.float32)], dim=-1) @ w_y.T + b_y
+    if not regression:
+        yy = (yy[:, None] > st["uniq"][None]).sum(-1).to(torch.float32)   # class rank, encoders.py:961-964
+    return torch.stack([yy, ind.to(torch.float32)], dim=-1) @ w_y.T + b_y
 
 
 # ---------------------------------------------------------------------------------------------
@@ -256,7 +265,16 @@ def layer_forward(state, n_train, sd, l, *, kv_in=None, want_kv=False):
     a = _attend(qkv[:, :, 0], qkv[:, :, 1], qkv[:, :, 2])           # over tokens
     state = _ln(state + torch.einsum("sthd,hde->ste", a, Of))       # :513-517, memory.py:99-100
     # --- attention between items (per token column) ---
-    Wi, Oi = sd[p + "self_attn_between_items._w_qkv"], sd[p + "self_attn_between_items._w_out"]
+    Oi = sd[p + "self_attn_between_items._w_out"]
+    if p + "self_attn_between_items._w_qkv" in sd:
+        Wi = sd[p + "self_attn_between_items._w_qkv"]
+        Wq_test = Wi[0]
+    else:
+        # two_sets_of_queries checkpoints (multi_head_attention.py:216-260, :418-419): query set 0 for the train
+        # rows, set 1 for the test rows (layer.py:357), keys / values from _w_kv
+        wq, wkv = sd[p + "self_attn_between_items._w_q"], sd[p + "self_attn_between_items._w_kv"]
+        Wi = torch.stack([wq[0], wkv[0], wkv[1]])
+        Wq_test = wq[wq.shape[0] - 1]
     xt = state.transpose(0, 1)                                      # [T, S, E]
     tr, te = xt[:, :n_train], xt[:, n_train:]
     outs, kv = [], None
@@ -270,7 +288,7 @@ def layer_forward(state, n_train, sd, l, *, kv_in=None, want_kv=False):
         kv0 = kv_in
     if te.shape[1] > 0:
         H = Wi.shape[1]
-        q = torch.einsum("tse,hde->tshd", te, Wi[0])
+        q = torch.einsum("tse,hde->tshd", te, Wq_test)
         k0 = kv0[:, :, 0][:, :, None].expand(-1, -1, H, -1)         # all q-heads share head 0
         v0 = kv0[:, :, 1][:, :, None].expand(-1, -1, H, -1)
         outs.append(_attend_chunked(q, k0, v0))
@@ -315,7 +333,7 @@ def forward_joint(X_full, img_full, y_train, sd, geom, *, seed=0, n_sigma=12.0, 
     if X_full is not None:
         tab_stats = stem_tab_fit(group_features(X_full.to(torch.float32), geom.features_per_group),
                                  n_train, n_sigma=n_sigma)
-    ey = stem_y(y_train, S, sd["y_encoder.2.layer.weight"], sd["y_encoder.2.layer.bias"])
+    ey = stem_y(y_train, S, *y_encoder_weights(sd))
     n_feat_tok = (0 if X_full is None else -(-X_full.shape[1] // geom.features_per_group)) + \
         (0 if img_full is None else n_image_tokens(img_full.shape[1], geom))
     embs = positional_embeddings(n_feat_tok, sd, geom, seed)
@@ -345,8 +363,7 @@ def forward_fit_context(X_train, img_train, y_train, sd, geom, *, seed=0, n_sigm
         tab_stats = stem_tab_fit(group_features(X_train.to(torch.float32), geom.features_per_group),
                                  n_train, n_sigma=n_sigma)
     yst = stem_y_fit(y_train)
-    ey = stem_y_apply(y_train.to(torch.float32), yst, sd["y_encoder.2.layer.weight"],
-                      sd["y_encoder.2.layer.bias"])
+    ey = stem_y_apply(y_train.to(torch.float32), yst, *y_encoder_weights(sd))
     n_feat_tok = (0 if X_train is None else -(-X_train.shape[1] // geom.features_per_group)) + \
         (0 if img_train is None else n_image_tokens(img_train.shape[1], geom))
     embs = positional_embeddings(n_feat_tok, sd, geom, seed)
@@ -362,8 +379,7 @@ def forward_fit_context(X_train, img_train, y_train, sd, geom, *, seed=0, n_sigm
 def forward_with_context(X_test, img_test, ctx, sd, geom):
     """Test rows only, against a cached context -> logits [Nte, n_out]."""
     n_te = X_test.shape[0] if X_test is not None else img_test.shape[0]
-    ey = stem_y_apply(torch.full((n_te,), float("nan")), ctx["y_stats"],
-                      sd["y_encoder.2.layer.weight"], sd["y_encoder.2.layer.bias"])
+    ey = stem_y_apply(torch.full((n_te,), float("nan")), ctx["y_stats"], *y_encoder_weights(sd))
     state = embed_rows(None if X_test is None else X_test.to(torch.float32), img_test, ey,
                        ctx["tab_stats"], ctx["embs"], sd, geom)
     for l in range(geom.nlayers):

@@ -41,49 +41,25 @@ MODEL_CASES = {
     "imageonly_tiny": (dict(mgm_heads=2, cap_heads=4), "tiny", 5, "imageonly"),
     "edge_tiny": (dict(mgm_heads=2, cap_heads=4), "tiny", 6, "edge"),
     "stress_tiny": (dict(mgm_heads=2, cap_heads=4), "tiny", 7, "stress"),
+    # a checkpoint with two_sets_of_queries (multi_head_attention.py:216-260): _w_q [2,..] + _w_kv for the item attention
+    "twosets_tiny": (dict(mgm_heads=2, cap_heads=4), "tiny", 8, "twosets"),
+    # a regression checkpoint (max_num_classes = 0): y-encoder without the class-rank step, 64-bucket decoder
+    "regression_tiny": (dict(mgm_heads=2, cap_heads=4, n_out=64), "tiny", 9, "regression"),
 }
 
 
-def mutate_inputs(kind, X, img):
-    """Edge cases the stem must survive (encoders.py:461-491, :515, :615): constant columns,
-    a heavy-NaN column, +-inf cells, heavy outliers, odd feature count."""
-    if kind == "noimage":
-        return X, None
-    if kind == "imageonly":
-        return None, img
-    if kind == "edge":
-        X = X.copy()
-        X = np.concatenate([X, X[:, :2] * 0 + 3.25], axis=1)        # two constant columns -> F'=23 (odd)
-        X[:, 1] = 7.0                                               # constant inside a mixed group
-        X[100::7, 18] = np.inf                                      # inf only in test rows: in train rows the
-        X[103::11, 19] = -np.inf                                    # reference itself raises (nanmean keeps inf)
-        X[5, 20] = 1e6                                              # outlier beyond 12 sigma
-        X[::3, 5] = np.nan                                          # heavy-NaN column
-        X[:, 4] = 2.0
-        X[100:, 4] = 3.0                                            # constant in train, varies in test
-        return X, img
-    return X, img
-
-
-def _snap(state):
-    """Keep 2 train + 2 test rows of a [1,S,T,E] state (fixtures stay small)."""
-    s = state[0]
-    return torch.cat([s[:2], s[-2:]], 0).numpy().copy()
-
-
-def run_model_case(name):
-    gkw, ds, wseed, mut = MODEL_CASES[name]
-    geom = Geometry(**{k: v for k, v in gkw.items() if v is not None or k == "cap_heads"})
-    extra = dict(residual_std=0.2, decoder_gain=20.0) if mut == "stress" else {}
-    sd = make_state_dict(geom, seed=wseed, **extra)
+def case_state_dict(geom, wseed, mut):
+    """The seeded synthetic weights + checkpoint config of a model case."""
+    sd, cfg = case_state_dict(geom, wseed, mut)
+    sd_model = {k: v for k, v in sd.items() if not k.startswith("criterion.")}
     model, _ = ref_compat.load_reference_model(
-        sd, make_checkpoint_config(geom), mixer_type=geom.mixer_type, mgm_heads=geom.mgm_heads,
+        sd, cfg, mixer_type=geom.mixer_type, mgm_heads=geom.mgm_heads,
         cap_heads=geom.cap_heads, features_per_group=geom.features_per_group, model_seed=0)
     d = make_dataset(ds, 0)
     X = np.concatenate([d["X_train"], d["X_test"]])
     img = np.concatenate([d["img_train"], d["img_test"]])
     X, img = mutate_inputs(mut, X, img)
-    y = d["y_train"].astype(np.float32)
+    y = case_targets(mut, d, X)
     n_tr = len(y)
 
     snaps = {}
@@ -182,10 +158,13 @@ def main():
     os.makedirs(OUT, exist_ok=True)
     torch.set_num_threads(8)
     assert os.environ.get("PYTHONHASHSEED") == "0", "run with PYTHONHASHSEED=0 (SURVEY.md gotcha 3)"
+    only = sys.argv[1:]
     for name in MODEL_CASES:
-        run_model_case(name)
+        if not only or name in only:
+            run_model_case(name)
     for name in CLF_CASES:
-        run_clf_case(name)
+        if not only or name in only:
+            run_clf_case(name)
 
 
 if __name__ == "__main__":

@@ -6,7 +6,7 @@ import numpy as np
 import torch
 
 from multimodalpfn_b200.synth import Geometry, make_dataset, make_state_dict
-from oracle.make_golden import CLF_CASES, MODEL_CASES, mutate_inputs
+from oracle.make_golden import CLF_CASES, MODEL_CASES, case_state_dict, case_targets, mutate_inputs
 
 GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
 
@@ -19,13 +19,12 @@ def model_case(name):
     """-> geom, state_dict(np), X_full(np|None), img_full(np|None), y_train(np f32), n_train"""
     gkw, ds, wseed, mut = MODEL_CASES[name]
     geom = Geometry(**{k: v for k, v in gkw.items() if v is not None or k == "cap_heads"})
-    extra = dict(residual_std=0.2, decoder_gain=20.0) if mut == "stress" else {}
-    sd = make_state_dict(geom, seed=wseed, **extra)
+    sd, _ = case_state_dict(geom, wseed, mut)
     d = make_dataset(ds, 0)
     X = np.concatenate([d["X_train"], d["X_test"]])
     img = np.concatenate([d["img_train"], d["img_test"]])
     X, img = mutate_inputs(mut, X, img)
-    y = d["y_train"].astype(np.float32)
+    y = case_targets(mut, d, X)
     return geom, sd, X, img, y, len(y)
 
 

@@ -234,3 +234,35 @@ def test_graph_replay_survives_scratch_growth():
         b = eng.logits_staged(staged).clone()
         assert torch.isfinite(a).all() and torch.equal(a, b), X.shape
         assert len(eng._graphs) <= eng.max_graphs
+
+
+@pytest.mark.parametrize("precision", ["fp32", "bf16"])
+@pytest.mark.parametrize("name", ["mgmcap_tiny", "twosets_tiny"])
+def test_reference_call_forms(name, precision):
+    """The reference's own call forms through ``__call__``: the model-level train-set cache
+    (``cache_trainset_representation``: train call, then ``y=None, single_eval_pos=None``; multi_head_attention.py:328-336)
+    against the reference's cached logits, and ``only_return_standard_out=False`` (transformer.py:855-867) against the
+    y-token of the reference's last-layer state."""
+    geom, sd, X, img, y, n_tr = model_case(name)
+    g = load_golden("model_" + name)
+    model = B200PerFeatureTransformer(sd, geom, precision=precision, seed=0)
+    tol = P_TOL[precision]
+    Xc, ic, yc = torch.as_tensor(X)[:, None].cuda(), torch.as_tensor(img).cuda(), torch.as_tensor(y).cuda()
+    model.cache_trainset_representation = True
+    out = model(None, Xc[:n_tr], ic[:n_tr], yc, only_return_standard_out=True, categorical_inds=[], single_eval_pos=n_tr)
+    assert tuple(out.shape) == (0, 1, geom.n_out)
+    lg = model(None, Xc[n_tr:], ic[n_tr:], None, only_return_standard_out=True, categorical_inds=[], single_eval_pos=None)
+    lg = lg.squeeze(1).cpu().numpy()
+    check_proba(softmax_np(lg[:, :3] / 0.9), softmax_np(g["logits_cached"][:, :3] / 0.9), tol, f"{name} cached call {precision}")
+    model.empty_trainset_representation_cache()
+    with pytest.raises(AssertionError):
+        model(None, Xc[n_tr:], ic[n_tr:], None, only_return_standard_out=True, categorical_inds=[], single_eval_pos=None)
+    model.cache_trainset_representation = False
+    d = model(None, Xc, ic, yc, only_return_standard_out=False, categorical_inds=[], single_eval_pos=n_tr)
+    assert set(d) == {"standard", "train_embeddings", "test_embeddings"}
+    assert tuple(d["train_embeddings"].shape) == (n_tr, 1, 192) and tuple(d["test_embeddings"].shape) == (X.shape[0] - n_tr, 1, 192)
+    ref_y = g["state_l11"][:, -1]                      # y-token of rows [0, 1, S-2, S-1] after the last layer
+    got = torch.cat([d["train_embeddings"][:2, 0], d["test_embeddings"][-2:, 0]]).cpu().numpy()
+    assert np.abs(got - ref_y).max() < (1e-4 if precision == "fp32" else 0.06)
+    check_proba(softmax_np(d["standard"].squeeze(1).cpu().numpy()[:, :3] / 0.9), softmax_np(g["logits"][:, :3] / 0.9), tol,
+                f"{name} dict output {precision}")
