@@ -50,8 +50,57 @@ MODEL_CASES = {
 
 def case_state_dict(geom, wseed, mut):
     """The seeded synthetic weights + checkpoint config of a model case."""
+    extra = dict(residual_std=0.2, decoder_gain=20.0) if mut == "stress" else {}
+    if mut == "twosets":
+        extra = dict(two_sets_of_queries=True)
+    if mut == "regression":
+        extra = dict(regression=True)
+    sd = make_state_dict(geom, seed=wseed, **extra)
+    cfg = make_checkpoint_config(geom, two_sets_of_queries=(mut == "twosets"), regression=(mut == "regression"))
+    return sd, cfg
+
+
+def case_targets(mut, d, X):
+    """Training targets of a model case: class ids, or (regression) a standardised continuous target."""
+    if mut == "regression":
+        rng = np.random.default_rng(77)
+        n = len(d["y_train"])
+        y = d["X_train"][:, 0] * 0.7 + d["y_train"] * 0.5 + 0.3 * rng.standard_normal(n)
+        return ((y - y.mean()) / y.std()).astype(np.float32)
+    return d["y_train"].astype(np.float32)
+
+
+def mutate_inputs(kind, X, img):
+    """Edge cases the stem must survive (encoders.py:461-491, :515, :615): constant columns,
+    a heavy-NaN column, +-inf cells, heavy outliers, odd feature count."""
+    if kind == "noimage":
+        return X, None
+    if kind == "imageonly":
+        return None, img
+    if kind == "edge":
+        X = X.copy()
+        X = np.concatenate([X, X[:, :2] * 0 + 3.25], axis=1)        # two constant columns -> F'=23 (odd)
+        X[:, 1] = 7.0                                               # constant inside a mixed group
+        X[100::7, 18] = np.inf                                      # inf only in test rows: in train rows the
+        X[103::11, 19] = -np.inf                                    # reference itself raises (nanmean keeps inf)
+        X[5, 20] = 1e6                                              # outlier beyond 12 sigma
+        X[::3, 5] = np.nan                                          # heavy-NaN column
+        X[:, 4] = 2.0
+        X[100:, 4] = 3.0                                            # constant in train, varies in test
+        return X, img
+    return X, img
+
+
+def _snap(state):
+    """Keep 2 train + 2 test rows of a [1,S,T,E] state (fixtures stay small)."""
+    s = state[0]
+    return torch.cat([s[:2], s[-2:]], 0).numpy().copy()
+
+
+def run_model_case(name):
+    gkw, ds, wseed, mut = MODEL_CASES[name]
+    geom = Geometry(**{k: v for k, v in gkw.items() if v is not None or k == "cap_heads"})
     sd, cfg = case_state_dict(geom, wseed, mut)
-    sd_model = {k: v for k, v in sd.items() if not k.startswith("criterion.")}
     model, _ = ref_compat.load_reference_model(
         sd, cfg, mixer_type=geom.mixer_type, mgm_heads=geom.mgm_heads,
         cap_heads=geom.cap_heads, features_per_group=geom.features_per_group, model_seed=0)

@@ -20,6 +20,7 @@ def model_case(name):
     gkw, ds, wseed, mut = MODEL_CASES[name]
     geom = Geometry(**{k: v for k, v in gkw.items() if v is not None or k == "cap_heads"})
     sd, _ = case_state_dict(geom, wseed, mut)
+    sd = {k: v for k, v in sd.items() if not k.startswith("criterion.")}      # (bar-distribution borders: host side)
     d = make_dataset(ds, 0)
     X = np.concatenate([d["X_train"], d["X_test"]])
     img = np.concatenate([d["img_train"], d["img_test"]])

@@ -73,3 +73,46 @@ def test_plugin_real_model_vs_reference(tmp_path, dataset, n_est, heads):
             check_proba(got, ref, tol + slack, f"plug-in[{mode}] {dataset} {precision} vs {what}")
     assert C.create_inference_engine.__name__ == "create_inference_engine"
     assert not getattr(C.create_inference_engine, "_mmpfn_b200", False)              # uninstalled
+
+
+@pytest.mark.parametrize("mode", ["engine", "model"])
+def test_plugin_regressor_vs_reference(tmp_path, mode):
+    """the reference's own ``MMPFNRegressor`` (target transforms, border translation,
+    bar-distribution mean / median / quantiles: regressor.py:390-730, model/bar_distribution.py — all its code) on a
+    regression checkpoint (y-encoder without the class-rank step, 64-bucket decoder) with this repo's engine plugged
+    in, against the reference's CPU fp32 ``predict``."""
+    from multimodalpfn_b200 import plugin
+    from multimodalpfn_b200.synth import Geometry, make_checkpoint_config, make_dataset, make_state_dict
+    ref_compat.install()
+    import mmpfn.models.mmpfn.regressor as R
+
+    geom = Geometry(mgm_heads=2, cap_heads=4, n_out=64)
+    sd = make_state_dict(geom, seed=9, regression=True)
+    path = str(tmp_path / "r.ckpt")
+    torch.save({"state_dict": {k: torch.as_tensor(v) for k, v in sd.items()},
+                "config": make_checkpoint_config(geom, regression=True)}, path)
+    d = make_dataset("tiny", 0)
+    rng = np.random.default_rng(0)
+    ytr = (d["X_train"][:, 0] * 0.7 + 0.3 * rng.standard_normal(len(d["X_train"]))).astype(np.float32)
+    kw = dict(mixer_type="MGM+CAP", mgm_heads=2, cap_heads=4, features_per_group=2, n_estimators=4, model_path=path,
+              ignore_pretraining_limits=True, random_state=0)
+
+    def run(**over):
+        reg = R.MMPFNRegressor(**{**kw, **over}).fit(d["X_train"], d["img_train"], ytr)
+        return reg, reg.predict(d["X_test"], d["img_test"], output_type="full")
+
+    with ref_compat.without_diagnostic_loop():
+        _, ref = run(device="cpu")
+    for precision, tol_logit, tol_mean in (("fp32", 2e-4, 2e-5), ("bf16", 0.05, 5e-3)):
+        uninstall = plugin.install(precision=precision, pos_emb_device="cpu", mode=mode)
+        try:
+            reg, got = run(device="cuda")
+        finally:
+            uninstall()
+        assert isinstance(reg.executor_, plugin.B200PluginEngine) == (mode == "engine")
+        dl = float((got["logits"] - ref["logits"]).abs().max())
+        dm = float(np.abs(got["mean"] - ref["mean"]).max())
+        dq = max(float(np.abs(a - b).max()) for a, b in zip(got["quantiles"], ref["quantiles"]))
+        print(f"[plug-in[{mode}] regressor {precision}] max |d log-prob| {dl:.3e}, |d mean| {dm:.3e}, |d quantile| {dq:.3e} "
+              f"(targets span {float(ytr.min()):.2f} .. {float(ytr.max()):.2f})")
+        assert dl < tol_logit and dm < tol_mean, (precision, dl, dm)
