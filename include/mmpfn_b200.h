@@ -87,6 +87,10 @@ typedef struct mmpfn_weights {
   const float* cap_f1_b;            /* [2E] */
   const float* cap_f2_w;            /* [E][2E] */
   const float* cap_f2_b;            /* [E] */
+  /* optional bf16 copy of mgm_w1 (MGM / MGM+CAP): when set and mgm_heads >= 32, the MGM gated projection — the stem's
+   * one large GEMM, M0 x (Hm*img) x img — runs on tcgen05 with bf16 operands and fp32 accumulation; NULL (or fewer
+   * heads) keeps it on the fp32 FFMA path (the 1e-5 parity mode) */
+  const uint16_t* mgm_w1_bf16;
 } mmpfn_weights;
 
 /* ---- introspection ------------------------------------------------------------------------- */

@@ -25,7 +25,7 @@ class Geometry(C.Structure):
 WEIGHT_FIELDS = ("layers_f32", "layers_bf16", "enc_w", "yenc_w", "yenc_b", "dec_w1", "dec_b1", "dec_w2", "dec_b2",
                  "mgm_w1", "mgm_b1", "mgm_w2", "mgm_b2", "moe_gate_w", "moe_gate_b", "cap_knorm_w", "cap_knorm_b",
                  "cap_q", "cap_wkv", "cap_bkv", "cap_wo", "cap_bo", "cap_onorm_w", "cap_onorm_b", "cap_f1_w",
-                 "cap_f1_b", "cap_f2_w", "cap_f2_b")
+                 "cap_f1_b", "cap_f2_w", "cap_f2_b", "mgm_w1_bf16")
 
 
 class Weights(C.Structure):

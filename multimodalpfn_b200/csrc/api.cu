@@ -194,6 +194,7 @@ int mmpfn_stem_tab_fit(const mmpfn_geometry* g, const float* x, int B, int S, in
 // image stem scratch (floats)
 struct ImgWs {
   float *xhat, *u, *src, *srcn, *kv, *o, *o2, *f1, *f2, *gl;
+  uint16_t* xhat_b;     // bf16 copy of the normalised embeddings: A operand of the tcgen05 MGM GEMM
   size_t bytes;
 };
 static ImgWs carve_img(const mmpfn_geometry* g, void* base, int S, int n_tok) {
@@ -212,6 +213,7 @@ static ImgWs carve_img(const mmpfn_geometry* g, void* base, int S, int n_tok) {
   } else {
     const size_t M0 = (size_t)S * n_tok, n_kv = Hm * n_tok, Hc = g->cap_heads;
     w.xhat = take(M0 * I);
+    w.xhat_b = (uint16_t*)take((M0 * I + 1) / 2);
     w.u = take(M0 * Hm * (I / 2));
     if (g->mixer_type == MMPFN_MIXER_MGM_CAP) {
       w.src = take((size_t)S * n_kv * kE);
@@ -263,8 +265,20 @@ int mmpfn_stem_image(const mmpfn_geometry* g, const mmpfn_weights* w, const floa
 
   const int M0 = S * n_tok, n_kv = Hm * n_tok;
   // MGM (transformer.py:33-48): LayerNorm statistics once, per-head affine folded into W1/b1
-  MMPFN_TRY(launch_layernorm(img, nullptr, nullptr, nullptr, M0, I, ws.xhat, nullptr, st));
-  MMPFN_TRY(launch_sgemm(gemm(ws.xhat, I, w->mgm_w1, I, w->mgm_b1, ws.u, Hm * Ih, M0, Hm * I, I), EPI_GLU_PAIR, st));
+  if (w->mgm_w1_bf16 && Hm >= 32) {
+    // bf16 mode, many MGM heads: the one large GEMM of the stem (M0 x Hm*768 x 768: 0.09 TFLOP per 300 rows at 256
+    // heads) on tcgen05, bias + GLU in the epilogue, fp32 out; everything downstream of it stays fp32.  Below 32 heads
+    // the FFMA GEMM takes < 0.1 ms per call and keeps the stem exact (measured: bf16 operands here cost 13 % of the
+    // bf16 error budget at trained-like logit scales, tests/test_gpu_model.py stress_tiny)
+    MMPFN_TRY(launch_layernorm(img, nullptr, nullptr, nullptr, M0, I, ws.xhat, ws.xhat_b, st));
+    TcGemm t{};
+    t.A = ws.xhat_b; t.W = w->mgm_w1_bf16; t.M = M0; t.N = Hm * I; t.K = I; t.epi = TC_EPI_GLU_PAIR_F32;
+    t.bias = w->mgm_b1; t.out_f32 = ws.u;
+    MMPFN_TRY(launch_tc_gemm(t, st));
+  } else {
+    MMPFN_TRY(launch_layernorm(img, nullptr, nullptr, nullptr, M0, I, ws.xhat, nullptr, st));
+    MMPFN_TRY(launch_sgemm(gemm(ws.xhat, I, w->mgm_w1, I, w->mgm_b1, ws.u, Hm * Ih, M0, Hm * I, I), EPI_GLU_PAIR, st));
+  }
   float* src = g->mixer_type == MMPFN_MIXER_MGM ? out : ws.src;
   {
     SgemmParams p = gemm(ws.u, Hm * Ih, w->mgm_w2, Ih, w->mgm_b2, src, kE, M0, kE, Ih);

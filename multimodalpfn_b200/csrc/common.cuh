@@ -139,7 +139,7 @@ struct ItemAttnF32 {
 int launch_item_attn_f32(const ItemAttnF32& p, cudaStream_t st);
 
 // ---- tcgen05 path (kernels_tc.cu) ------------------------------------------------------------
-enum { TC_EPI_BF16 = 0, TC_EPI_GELU_BF16 = 1, TC_EPI_RESID_LN = 2, TC_EPI_QKV_ITEMS = 3 };
+enum { TC_EPI_BF16 = 0, TC_EPI_GELU_BF16 = 1, TC_EPI_RESID_LN = 2, TC_EPI_QKV_ITEMS = 3, TC_EPI_GLU_PAIR_F32 = 4 };
 struct TcGemm {
   const uint16_t* A;   // bf16 activations; FLAT: [M][K]; ITEMS: state [B][S][T][K]
   const uint16_t* W;   // bf16 [N][K]
@@ -157,6 +157,9 @@ struct TcGemm {
   int S_pad;
   // optional head-0 context for this layer: k0 [B][T][S_pad][kD], vt0 [B][T][kD][S_pad]
   uint16_t *k0_out, *vt0_out;
+  // TC_EPI_GLU_PAIR_F32 (kernels_tc.cu only): columns (2c, 2c+1) = (value, gate) + bias -> out_f32[m][c] = value * sigmoid(gate)
+  const float* bias;
+  float* out_f32;      // [M][N/2]
 };
 int launch_tc_gemm(const TcGemm& p, cudaStream_t st);
 // persistent variant for K = 192, N % 192 == 0 (kernels_rowgemm.cu): BF16 / RESID_LN / QKV_ITEMS epilogues

@@ -34,6 +34,8 @@ struct GemmArgs {
   uint16_t* ln_bf16;
   uint16_t *q_out, *k_out, *vt_out, *k0_out, *vt0_out;
   int S_pad;
+  const float* bias;
+  float* out_f32;
 };
 
 template <int EPI>
@@ -139,6 +141,29 @@ __global__ void __launch_bounds__(G_THREADS) tc_gemm_kernel(const __grid_constan
           uint4* d4 = reinterpret_cast<uint4*>(dst + c * 32);
 #pragma unroll
           for (int i = 0; i < 4; ++i) d4[i] = make_uint4(pk[4 * i], pk[4 * i + 1], pk[4 * i + 2], pk[4 * i + 3]);
+        }
+      }
+    } else if (EPI == TC_EPI_GLU_PAIR_F32) {
+      // nn.GLU of the MGM stem (transformer.py:38-41): adjacent columns are (value, gate); fp32 out [M][N/2]
+      const long long m = (long long)m0 + r;
+      const bool ok = m < p.M;
+      float* dst = p.out_f32 + m * (p.N / 2) + n0 / 2;
+      const float* bias = p.bias + n0;
+#pragma unroll 1
+      for (int c = 0; c < G_BN / 32; ++c) {
+        tmem_ld32(trow + c * 32, v);
+        tmem_ld_wait();
+        if (ok) {
+          float o[16];
+#pragma unroll
+          for (int i = 0; i < 16; ++i) {
+            const float a = __uint_as_float(v[2 * i]) + __ldg(bias + c * 32 + 2 * i);
+            const float g = __uint_as_float(v[2 * i + 1]) + __ldg(bias + c * 32 + 2 * i + 1);
+            o[i] = a * (1.0f / (1.0f + __expf(-g)));
+          }
+          float4* d4 = reinterpret_cast<float4*>(dst + c * 16);
+#pragma unroll
+          for (int i = 0; i < 4; ++i) d4[i] = make_float4(o[4 * i], o[4 * i + 1], o[4 * i + 2], o[4 * i + 3]);
         }
       }
     } else if (EPI == TC_EPI_RESID_LN) {
@@ -258,6 +283,8 @@ int launch_tc_gemm(const TcGemm& p, cudaStream_t st) {
   a.out_bf16 = p.out_bf16; a.resid = p.resid_f32; a.ln_bf16 = p.ln_bf16;
   a.q_out = p.q_out; a.k_out = p.k_out; a.vt_out = p.vt_out; a.k0_out = p.k0_out; a.vt0_out = p.vt0_out;
   a.S_pad = p.S_pad;
+  a.bias = p.bias; a.out_f32 = p.out_f32;
+  if (p.epi == TC_EPI_GLU_PAIR_F32 && (!p.bias || !p.out_f32)) { set_error("tc_gemm: GLU epilogue needs bias and fp32 output"); return MMPFN_EINVAL; }
   CUtensorMap ma, mw;
   dim3 grid;
   if (p.items) {
@@ -287,6 +314,7 @@ int launch_tc_gemm(const TcGemm& p, cudaStream_t st) {
     case TC_EPI_GELU_BF16: return launch_gemm_t<TC_EPI_GELU_BF16>(ma, mw, a, grid, st);
     case TC_EPI_RESID_LN: return launch_gemm_t<TC_EPI_RESID_LN>(ma, mw, a, grid, st);
     case TC_EPI_QKV_ITEMS: return launch_gemm_t<TC_EPI_QKV_ITEMS>(ma, mw, a, grid, st);
+    case TC_EPI_GLU_PAIR_F32: return launch_gemm_t<TC_EPI_GLU_PAIR_F32>(ma, mw, a, grid, st);
   }
   set_error("tc_gemm: bad epilogue %d", p.epi);
   return MMPFN_EINVAL;

@@ -72,7 +72,7 @@ class B200PerFeatureTransformer:
         self.outlier_std = outlier_std
         self.pos_emb_device = pos_emb_device
         with torch.cuda.device(self.device):
-            self.w = PackedWeights(state_dict, geom, self.device, with_bf16=True)
+            self.w = PackedWeights(state_dict, geom, self.device, with_bf16=True, stem_bf16=(precision == "bf16"))
         self._g = C.byref(self.w.c_geom)
         self._w = C.byref(self.w.c_weights)
         self._w_test = C.byref(self.w.c_weights_test)      # second query set of two_sets_of_queries checkpoints

@@ -37,7 +37,8 @@ def _ln64(x, g, b, eps=1e-5):
 class PackedWeights:
     """Device-resident weights + the ctypes structs the C ABI takes."""
 
-    def __init__(self, state_dict, geom: Geometry, device: torch.device, *, with_bf16: bool = True):
+    def __init__(self, state_dict, geom: Geometry, device: torch.device, *, with_bf16: bool = True,
+                 stem_bf16: bool = True):
         sd = {k: _np(v).astype(np.float64) for k, v in state_dict.items()}
         self.geom = geom
         self.device = torch.device(device)
@@ -120,6 +121,9 @@ class PackedWeights:
             put("mgm_b1", np.concatenate(b1s, 0))
             put("mgm_w2", np.stack(w2s, 0))
             put("mgm_b2", np.stack(b2s, 0))
+            if with_bf16 and stem_bf16:
+                # operand of the tcgen05 MGM GEMM (bf16 mode only; the fp32 mode keeps the FFMA path for the 1e-5 gate)
+                self._t["mgm_w1_bf16"] = self._t["mgm_w1"].to(torch.bfloat16)
         if geom.mixer_type == "MoE":
             w1s, b1s, w2s, b2s = [], [], [], []
             for h in range(geom.mgm_heads):

@@ -43,6 +43,10 @@ MODEL_CASES = {
     "stress_tiny": (dict(mgm_heads=2, cap_heads=4), "tiny", 7, "stress"),
     # a checkpoint with two_sets_of_queries (multi_head_attention.py:216-260): _w_q [2,..] + _w_kv for the item attention
     "twosets_tiny": (dict(mgm_heads=2, cap_heads=4), "tiny", 8, "twosets"),
+    # the head counts of the authors' best PAD-UFES cell is (256, 24) (mmpfn/charts/pad_ufes_20.csv:36); (64, 24) is the
+    # geometry of their fine-tuning log (50.2 M parameters, mmpfn/logs/finetune_tabpfn.log:6): CAP head_dim = 8,
+    # 64 MGM tokens per embedding
+    "mgm64_cap24_tiny": (dict(mgm_heads=64, cap_heads=24), "tiny", 10, None),
     # a regression checkpoint (max_num_classes = 0): y-encoder without the class-rank step, 64-bucket decoder
     "regression_tiny": (dict(mgm_heads=2, cap_heads=4, n_out=64), "tiny", 9, "regression"),
 }

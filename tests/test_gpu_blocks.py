@@ -204,6 +204,23 @@ def test_feature_attention_bf16(n_rows, T):
     assert (att.float() - ref).abs().max().item() < 0.03      # P and the output rounded to bf16, O(1) values
 
 
+@pytest.mark.parametrize("mgm,cap,rows,n_tok", [(2, 4, 77, 1), (8, 8, 300, 2), (64, 24, 130, 1)])
+def test_image_stem_bf16_vs_fp32(mgm, cap, rows, n_tok):
+    """MGM + CAP stem (transformer.py:33-88): the bf16 mode (gated projection on tcgen05, bf16 operands) against the
+    fp32 mode of the same library (FFMA, itself held to 2e-5 of the reference by test_stem_state_vs_golden), at the
+    default head counts and at the authors' 64 / 24 geometry (CAP head_dim 8)."""
+    from multimodalpfn_b200.model import B200PerFeatureTransformer
+    geom = Geometry(nlayers=1, mgm_heads=mgm, cap_heads=cap)
+    sd = make_state_dict(geom, seed=4)
+    img = torch.randn(rows, n_tok, 768, generator=torch.Generator().manual_seed(rows)).cuda()
+    a = B200PerFeatureTransformer(sd, geom, precision="fp32").stem_image(img)
+    b = B200PerFeatureTransformer(sd, geom, precision="bf16").stem_image(img)
+    assert tuple(a.shape) == (rows, cap, 192) and torch.isfinite(b).all()
+    err = float((a - b).abs().max())
+    # below 32 MGM heads both modes take the FFMA path (identical); above, bf16 operand rounding and nothing else
+    assert (err == 0.0) if mgm < 32 else (0 < err < 0.03 * max(1.0, float(a.abs().max()))), err
+
+
 def _one_layer_model(precision, seed=3):
     from multimodalpfn_b200.model import B200PerFeatureTransformer
     geom = Geometry(nlayers=1, mgm_heads=2, cap_heads=4)
