@@ -195,12 +195,30 @@ typedef struct mmpfn_kv_segment {
   void* kv;
   int64_t layer_stride;   /* bytes */
   int32_t slots;
-  int32_t reserved;
+  int32_t seg_rows;       /* > 0: row-sharded context (below); 0: off */
   int64_t rank_stride;    /* bytes */
+  /* Row-sharded context build: the train rows of ONE estimator batch are split over the
+   * ranks, seg_rows rows per rank (a multiple of 48: key tiles then never straddle two ranks and are exactly the
+   * tiles of the unsharded layout — results are bit-identical).  Every rank runs the row-wise sublayers on its own
+   * rows; for the item attention its rows' K / V^T planes are written into chunk `rank` of the caller's gather buffers
+   *     kg  [n_ranks][B*T*6][Sp][32]      vtg [n_ranks][B*T*6][32][Sp]      (Sp = S rounded up to 64, bf16;
+   *     gather_stride bytes between chunks; pad rows must hold finite values: zero the buffers once)
+   * in phase 1, the caller all-gathers both buffers, and in phase 2 the rank's queries attend to all n_rows_total
+   * keys.  The head-0 context block of the layer (at kv + l * layer_stride, layout as above with c = B) holds this
+   * rank's rows only; gathered over the ranks (chunks rank_stride apart) it is what the TEST pass reads when its
+   * segment has seg_rows > 0: estimator b's keys = chunks 0..n_ranks-1, seg_rows rows each. */
+  void* kg;
+  void* vtg;
+  int64_t gather_stride;  /* bytes */
+  int32_t rank, n_ranks;
+  int32_t n_rows_total;
+  int32_t reserved;
 } mmpfn_kv_segment;
+/* phase: 0 = whole layers; 1 = layer `layer_begin` up to and including the item-attention QKV projection;
+ * 2 = the rest of that layer (phases 1 / 2 need layer_end == layer_begin + 1). */
 int mmpfn_layers_run(const mmpfn_geometry* g, const mmpfn_weights* w, float* state_f32, uint16_t* state_bf16,
                      const mmpfn_kv_segment* segs, int n_seg, int S, int n_train, int train, int layer_begin,
-                     int layer_end, void* workspace, size_t workspace_bytes, void* stream);
+                     int layer_end, int phase, void* workspace, size_t workspace_bytes, void* stream);
 
 /* ---- decoder + probability tail ------------------------------------------------------------ */
 /* transformer.py:392-396, :850-853: logits[b][s][:] = W2 gelu(W1 state[b][s][T-1] + b1) + b2.

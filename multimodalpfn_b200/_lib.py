@@ -39,7 +39,9 @@ class Segment(C.Structure):
 class KvSegment(C.Structure):
     """mmpfn_kv_segment (include/mmpfn_b200.h)"""
     _fields_ = [("B", C.c_int32), ("T", C.c_int32), ("kv", C.c_void_p), ("layer_stride", C.c_int64),
-                ("slots", C.c_int32), ("reserved", C.c_int32), ("rank_stride", C.c_int64)]
+                ("slots", C.c_int32), ("seg_rows", C.c_int32), ("rank_stride", C.c_int64),
+                ("kg", C.c_void_p), ("vtg", C.c_void_p), ("gather_stride", C.c_int64), ("rank", C.c_int32),
+                ("n_ranks", C.c_int32), ("n_rows_total", C.c_int32), ("reserved", C.c_int32)]
 
 
 PG, PW = C.POINTER(Geometry), C.POINTER(Weights)
@@ -66,8 +68,8 @@ SIGNATURES = {
     "mmpfn_layers_train_multi": (c_int, [PG, PW, c_void_p, c_void_p, PS, c_int, c_int, PVP, c_void_p, c_size_t, c_void_p]),
     "mmpfn_layers_test_multi": (c_int, [PG, PW, c_void_p, c_void_p, PS, c_int, c_int, c_int, PVP, c_void_p, c_size_t,
                                         c_void_p]),
-    "mmpfn_layers_run": (c_int, [PG, PW, c_void_p, c_void_p, PKS, c_int, c_int, c_int, c_int, c_int, c_int, c_void_p,
-                                 c_size_t, c_void_p]),
+    "mmpfn_layers_run": (c_int, [PG, PW, c_void_p, c_void_p, PKS, c_int, c_int, c_int, c_int, c_int, c_int, c_int,
+                                 c_void_p, c_size_t, c_void_p]),
     "mmpfn_layers_train": (c_int, [PG, PW, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p,
                                    c_size_t, c_void_p]),
     "mmpfn_layers_test": (c_int, [PG, PW, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_void_p, c_void_p,

@@ -556,7 +556,7 @@ static size_t kv_block_elems(int c, int T, int n_pad) { return (size_t)2 * c * T
 // train == 0: the S rows are test rows attending to the n_train rows' context segs[i].kv
 static int layers_run(const mmpfn_geometry* g, const mmpfn_weights* w, float* state, uint16_t* state_b,
                       const mmpfn_kv_segment* ks, int n_seg, int S, int n_train, int train, int layer_begin,
-                      int layer_end, void* workspace, size_t workspace_bytes, cudaStream_t st) {
+                      int layer_end, int phase, void* workspace, size_t workspace_bytes, cudaStream_t st) {
   MMPFN_TRY(check_geometry(g));
   MMPFN_TRY(require_device());
   if (!ks || n_seg < 1 || n_seg > MMPFN_MAX_SEGMENTS) { set_error("layers_run: bad segment list"); return MMPFN_EINVAL; }
@@ -566,16 +566,29 @@ static int layers_run(const mmpfn_geometry* g, const mmpfn_weights* w, float* st
   MMPFN_TRY(check_segments(segs, n_seg, S, &M));
   if (!w || !w->layers_f32 || !w->layers_bf16 || !state || !state_b) { set_error("layers_run: null argument (bf16 mode only)"); return MMPFN_EINVAL; }
   if (layer_begin < 0 || layer_end > g->nlayers || layer_begin >= layer_end) { set_error("layers_run: bad layer range [%d, %d)", layer_begin, layer_end); return MMPFN_EINVAL; }
+  if (phase < 0 || phase > 2 || (phase != 0 && layer_end != layer_begin + 1)) { set_error("layers_run: phase %d needs a single layer", phase); return MMPFN_EINVAL; }
+  for (int i = 0; i < n_seg; ++i) {
+    const mmpfn_kv_segment& k = ks[i];
+    if (train && k.seg_rows > 0 && (!k.kg || !k.vtg || k.n_ranks < 1 || k.rank < 0 || k.rank >= k.n_ranks || k.seg_rows % 48 != 0 ||
+                                    S > k.seg_rows || k.n_rows_total < 1 || k.gather_stride % 16 != 0)) {
+      set_error("layers_run: bad row-sharding description of segment %d", i);
+      return MMPFN_EINVAL;
+    }
+  }
   if (!train) for (int i = 0; i < n_seg; ++i) if (!ks[i].kv || n_train < 1) { set_error("layers_run: the test pass needs every segment's context"); return MMPFN_EINVAL; }
-  MultiWs ws = carve_multi(workspace, segs, n_seg, S, M);
+  // row-sharded build: every rank lays its planes out for seg_rows rows (the last rank holds fewer), so that the
+  // chunks of the gather buffers and of the gathered context have one plane stride
+  int Sa = S;
+  if (train) for (int i = 0; i < n_seg; ++i) if (ks[i].seg_rows > Sa) Sa = ks[i].seg_rows;
+  MultiWs ws = carve_multi(workspace, segs, n_seg, Sa, M);
   if (!workspace || workspace_bytes < ws.bytes) { set_error("layers_run: workspace %zu < %zu bytes", workspace_bytes, ws.bytes); return MMPFN_EINVAL; }
-  const int Sp = kv_pad(S), Np = kv_pad(n_train);
+  const int Sp = kv_pad(Sa), Np = kv_pad(n_train);
   LayerWs flat{};
   flat.hid_b = ws.hid_b; flat.qkv_b = ws.hid_b; flat.att_b = ws.att_b;
   for (int l = layer_begin; l < layer_end; ++l) {
     const LayerW lw = layer_w(w, l);
     // features: QKV over all tokens, attention per segment (rows of T_i tokens), out-projection + LN over all
-    {
+    if (phase != 2) {
       TcGemm a{};
       a.A = state_b; a.W = lw.fqkv_b; a.M = (int)M; a.N = 3 * kE; a.K = kE; a.epi = TC_EPI_BF16; a.out_bf16 = ws.hid_b;
       MMPFN_TRY(proj_gemm(a, st));
@@ -599,7 +612,23 @@ static int layers_run(const mmpfn_geometry* g, const mmpfn_weights* w, float* st
         q.epi = TC_EPI_QKV_ITEMS; q.q_out = ws.seg[i].qi; q.S_pad = Sp;
         TcItemAttn a{};
         a.q = ws.seg[i].qi; a.out = ws.att_b + off * kE; a.B = B; a.T = T; a.n_q = S; a.Sq_pad = Sp;
-        if (train) {
+        const bool rows_mode = train && ks[i].seg_rows > 0;
+        if (rows_mode) {
+          // row-sharded build: this rank's K / V^T planes go into its chunk of the gather buffers; after the
+          // caller's all-gather the attention reads every chunk as one key range of n_rows_total rows
+          uint16_t* kg = (uint16_t*)ks[i].kg;
+          uint16_t* vg = (uint16_t*)ks[i].vtg;
+          const size_t cs = (size_t)ks[i].gather_stride / 2;
+          q.k_out = kg + cs * ks[i].rank; q.vt_out = vg + cs * ks[i].rank;
+          if (ks[i].kv) {
+            const size_t stride = ks[i].layer_stride > 0 ? (size_t)ks[i].layer_stride / 2 : kv_block_elems(B, T, Sp);
+            uint16_t* kvl = (uint16_t*)ks[i].kv + (size_t)l * stride;
+            q.k0_out = kvl;
+            q.vt0_out = kvl + (size_t)B * T * Sp * kD;
+          }
+          a.k = kg; a.vt = vg; a.n_kv = ks[i].n_rows_total; a.Skv_pad = Sp; a.shared_kv = 0;
+          a.kv_seg_rows = ks[i].seg_rows; a.kv_seg_stride = (long long)cs;
+        } else if (train) {
           q.k_out = ws.seg[i].ki; q.vt_out = ws.seg[i].vti;
           if (ks[i].kv) {
             const size_t stride = ks[i].layer_stride > 0 ? (size_t)ks[i].layer_stride / 2 : kv_block_elems(B, T, Sp);
@@ -615,14 +644,21 @@ static int layers_run(const mmpfn_geometry* g, const mmpfn_weights* w, float* st
           a.k = kvl; a.vt = kvl + (size_t)c * T * Np * kD; a.n_kv = n_train; a.Skv_pad = Np; a.shared_kv = 1;
           a.kv_slots = ks[i].slots > 0 ? ks[i].slots : 0;
           a.kv_rank_stride = ks[i].rank_stride / 2;
+          if (ks[i].seg_rows > 0) {
+            // the context was built row-sharded: chunk r (rank_stride apart) holds rows [r * seg_rows, ...) of every
+            // estimator, each chunk laid out K0 [B][T][Sp_loc][32] then V0^T [B][T][32][Sp_loc]
+            const int Sl = kv_pad(ks[i].seg_rows);
+            a.Skv_pad = Sl; a.vt = kvl + (size_t)B * T * Sl * kD; a.kv_slots = 0;
+            a.kv_seg_rows = ks[i].seg_rows; a.kv_seg_stride = ks[i].rank_stride / 2;
+          }
         }
-        MMPFN_TRY(proj_gemm(q, st));
-        MMPFN_TRY(launch_tc_item_attn(a, st));
+        if (phase != 2) MMPFN_TRY(proj_gemm(q, st));
+        if (phase != 1) MMPFN_TRY(launch_tc_item_attn(a, st));
         off += (long long)B * S * T;
       }
-      MMPFN_TRY(out_proj_ln(lw, state, state_b, M, MMPFN_BF16, flat, st));
+      if (phase != 1) MMPFN_TRY(out_proj_ln(lw, state, state_b, M, MMPFN_BF16, flat, st));
     }
-    MMPFN_TRY(mlp(lw, state, state_b, M, MMPFN_BF16, flat, st));
+    if (phase != 1) MMPFN_TRY(mlp(lw, state, state_b, M, MMPFN_BF16, flat, st));
   }
   return MMPFN_OK;
 }
@@ -633,10 +669,10 @@ static int layers_multi(const mmpfn_geometry* g, const mmpfn_weights* w, float* 
   if (!segs || !kv || n_seg < 1 || n_seg > MMPFN_MAX_SEGMENTS || !g) { set_error("layers_multi: bad segment list"); return MMPFN_EINVAL; }
   mmpfn_kv_segment ks[MMPFN_MAX_SEGMENTS];
   for (int i = 0; i < n_seg; ++i) {
-    ks[i].B = segs[i].B; ks[i].T = segs[i].T; ks[i].kv = kv[i]; ks[i].layer_stride = 0; ks[i].slots = 0; ks[i].reserved = 0;
-    ks[i].rank_stride = 0;
+    ks[i] = mmpfn_kv_segment{};
+    ks[i].B = segs[i].B; ks[i].T = segs[i].T; ks[i].kv = kv[i];
   }
-  return layers_run(g, w, state, state_b, ks, n_seg, S, n_train, train, 0, g->nlayers, workspace, workspace_bytes, st);
+  return layers_run(g, w, state, state_b, ks, n_seg, S, n_train, train, 0, g->nlayers, 0, workspace, workspace_bytes, st);
 }
 
 int mmpfn_layers_train_multi(const mmpfn_geometry* g, const mmpfn_weights* w, float* state_f32, uint16_t* state_bf16,
@@ -653,8 +689,8 @@ int mmpfn_layers_test_multi(const mmpfn_geometry* g, const mmpfn_weights* w, flo
 
 int mmpfn_layers_run(const mmpfn_geometry* g, const mmpfn_weights* w, float* state_f32, uint16_t* state_bf16,
                      const mmpfn_kv_segment* segs, int n_seg, int S, int n_train, int train, int layer_begin,
-                     int layer_end, void* workspace, size_t workspace_bytes, void* stream) {
-  return layers_run(g, w, state_f32, state_bf16, segs, n_seg, S, n_train, train, layer_begin, layer_end, workspace,
+                     int layer_end, int phase, void* workspace, size_t workspace_bytes, void* stream) {
+  return layers_run(g, w, state_f32, state_bf16, segs, n_seg, S, n_train, train, layer_begin, layer_end, phase, workspace,
                     workspace_bytes, (cudaStream_t)stream);
 }
 

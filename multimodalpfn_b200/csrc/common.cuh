@@ -188,6 +188,12 @@ struct TcItemAttn {
   // estimator b = (rank b / c, slot b % c), its plane t at  rank * kv_rank_stride + (slot*T + t) planes  (elements).
   int kv_slots;
   long long kv_rank_stride;
+  // Row segments (row-sharded context build, dist.py "rows" mode): the n_kv keys are stored as ceil(n_kv /
+  // kv_seg_rows) chunks of kv_seg_rows rows (a multiple of the 48-key tile, so that no tile straddles two chunks
+  // and the tiles are exactly those of the unsegmented layout), kv_seg_stride elements apart; inside a chunk the
+  // planes are laid out as usual with Skv_pad allocated rows.  0 = one contiguous row range.
+  int kv_seg_rows;
+  long long kv_seg_stride;
 };
 int launch_tc_item_attn(const TcItemAttn& p, cudaStream_t st);
 

@@ -79,6 +79,7 @@ struct AttnArgs {
   int T, n_q, n_kv, shared_kv, q_tiles;
   int stack_rows;   // > 0: the six query heads of a (b, t) column are stacked on the tile's row axis, Sq_pad rows each
   int kv_slots;     // shared_kv: estimators per rank chunk of the K/V context (>= 1; B when the context is dense)
+  int tiles_per_seg;   // key tiles per row segment (row-sharded context: keys stored in per-rank chunks); 2^30 = one range
 };
 
 #ifdef MMPFN_DEBUG
@@ -300,19 +301,30 @@ __global__ void __launch_bounds__(A_THREADS, AttnCfg<BK>::kMinCtas)
     if (elect_one()) {
       mbar_expect_tx_addr(q_full, A_Q_BYTES + (nkt > 1 ? 2 : 1) * C::kKTx);
       tma_load_3d_addr(sbase, &map_q, q_full, 0, q0, plane);
-      tma_load_5d_addr(sbase + C::kOffK, &map_k, q_full, 0, 0, kc2, kc3, kc4);
-      if (nkt > 1) tma_load_5d_addr(sbase + C::kOffK + C::kKSlot, &map_k, q_full, 0, BK, kc2, kc3, kc4);
+      // key tile j = rows [row, row + BK) of row segment seg (one segment unless the context build is row-sharded)
+      const int tps = p.tiles_per_seg;
+      auto seg_of = [&](int j, int& row) { const int sg = j / tps; row = (j - sg * tps) * BK; return sg; };
+      int row, sg = seg_of(0, row);
+      tma_load_5d_addr(sbase + C::kOffK, &map_k, q_full, 0, row, kc2, kc3 + sg, kc4);
+      if (nkt > 1) {
+        sg = seg_of(1, row);
+        tma_load_5d_addr(sbase + C::kOffK + C::kKSlot, &map_k, q_full, 0, row, kc2, kc3 + sg, kc4);
+      }
       // refill g: V^T(g) and K(g+2) into slot g & 1 once done[g & 1] has completed g/2 + 1 times
       for (int g = 0; g < nkt; ++g) {
         const uint32_t s = g & 1;
         const bool has_k = g + 2 < nkt;
         mbar_wait_lean(done + s * 8, (g >> 1) & 1);
         mbar_expect_tx_addr(kv_full + s * 8, C::kVtBytes + (has_k ? C::kKTx : 0));
+        sg = seg_of(g, row);
 #pragma unroll
         for (int kb = 0; kb < C::kNKB; ++kb)
           tma_load_5d_addr(sbase + C::kOffVt + s * C::kVtBytes + kb * (kD * 128), &map_vt, kv_full + s * 8,
-                           g * BK + kb * 64, 0, kc2, kc3, kc4);
-        if (has_k) tma_load_5d_addr(sbase + C::kOffK + s * C::kKSlot, &map_k, kv_full + s * 8, 0, (g + 2) * BK, kc2, kc3, kc4);
+                           row + kb * 64, 0, kc2, kc3 + sg, kc4);
+        if (has_k) {
+          sg = seg_of(g + 2, row);
+          tma_load_5d_addr(sbase + C::kOffK + s * C::kKSlot, &map_k, kv_full + s * 8, 0, row, kc2, kc3 + sg, kc4);
+        }
       }
     }
   } else if (warp == 5) {
@@ -567,12 +579,25 @@ int launch_tc_item_attn(const TcItemAttn& p, cudaStream_t st) {
     const cuuint32_t box[3] = {kD, A_BQ, 1};
     MMPFN_TRY(encode_map(&mq, p.q, 3, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_64B));
   }
-  // K / V^T: {.., .., c2, c3, c4} = (plane, 0, 0) for own planes; (token column, slot, rank) for the shared context
-  int slots = 1;
+  // K / V^T: {.., rows, c2, c3, c4} = (plane, row segment, 0) for own planes; for the shared context
+  // (token column, slot, rank) when it sits in the estimator gather buffer or (token column, row segment, estimator)
+  // when it was built row-sharded
+  int slots = 1, tiles_per_seg = 1 << 30;
   cuuint64_t n2 = (cuuint64_t)planes_kv, n3 = 1, n4 = 1;
   const cuuint64_t plane_bytes = (cuuint64_t)p.Skv_pad * kD * 2;
   cuuint64_t s3 = plane_bytes * n2, s4 = plane_bytes * n2;
-  if (p.shared_kv) {
+  cuuint64_t rows_extent = (cuuint64_t)p.n_kv;
+  if (p.kv_seg_rows > 0) {
+    if (p.kv_seg_rows % BK != 0 || p.kv_seg_rows > p.Skv_pad || p.kv_slots > 0 || (p.kv_seg_stride * 2) % 16 != 0) {
+      set_error("item attention: row segments of %d rows (must be a multiple of %d, <= %d allocated rows)", p.kv_seg_rows, BK, p.Skv_pad);
+      return MMPFN_EINVAL;
+    }
+    tiles_per_seg = p.kv_seg_rows / BK;
+    rows_extent = (cuuint64_t)p.kv_seg_rows;      // pad rows of a short last segment are read: the caller keeps them finite
+    n3 = (cuuint64_t)((p.n_kv + p.kv_seg_rows - 1) / p.kv_seg_rows);
+    s3 = (cuuint64_t)p.kv_seg_stride * 2;
+    if (p.shared_kv) { n2 = (cuuint64_t)p.T; n4 = (cuuint64_t)p.B; s4 = plane_bytes * p.T; }
+  } else if (p.shared_kv) {
     slots = p.kv_slots > 0 ? p.kv_slots : p.B;
     if (p.B % slots != 0) { set_error("item attention: %d estimators do not fill chunks of %d", p.B, slots); return MMPFN_EINVAL; }
     n2 = (cuuint64_t)p.T; n3 = (cuuint64_t)slots; n4 = (cuuint64_t)(p.B / slots);
@@ -581,18 +606,18 @@ int launch_tc_item_attn(const TcItemAttn& p, cudaStream_t st) {
     if (s4 % 16 != 0 || (n4 > 1 && s4 < s3 * slots)) { set_error("item attention: bad rank stride of the K/V context"); return MMPFN_EINVAL; }
   }
   {
-    const cuuint64_t dims[5] = {(cuuint64_t)kD, (cuuint64_t)p.n_kv, n2, n3, n4};
+    const cuuint64_t dims[5] = {(cuuint64_t)kD, rows_extent, n2, n3, n4};
     const cuuint64_t strides[4] = {(cuuint64_t)kD * 2, plane_bytes, s3, s4};
     const cuuint32_t box[5] = {kD, BK, 1, 1, 1};
     MMPFN_TRY(encode_map(&mk, p.k, 5, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_64B));
   }
   {
-    const cuuint64_t dims[5] = {(cuuint64_t)p.n_kv, (cuuint64_t)kD, n2, n3, n4};
+    const cuuint64_t dims[5] = {rows_extent, (cuuint64_t)kD, n2, n3, n4};
     const cuuint64_t strides[4] = {(cuuint64_t)p.Skv_pad * 2, plane_bytes, s3, s4};
     const cuuint32_t box[5] = {64, kD, 1, 1, 1};
     MMPFN_TRY(encode_map(&mvt, p.vt, 5, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_128B));
   }
-  AttnArgs a{p.out, p.T, p.n_q, p.n_kv, p.shared_kv, q_tiles, stack ? p.Sq_pad : 0, slots};
+  AttnArgs a{p.out, p.T, p.n_q, p.n_kv, p.shared_kv, q_tiles, stack ? p.Sq_pad : 0, slots, tiles_per_seg};
   const dim3 grid((unsigned)(grid_planes * q_tiles));
 #ifdef MMPFN_DEBUG
   // tuning builds only (-DMMPFN_DEBUG): MMPFN_ATTN_PP = polynomial pairs of every 24.  The product

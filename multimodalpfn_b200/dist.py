@@ -129,8 +129,13 @@ class ShardedEngine:
     """Wraps a ``B200InferenceEngine``: contexts are built by their owner ranks and all-gathered layer by
     layer under the build; every rank runs its own test rows against all of them."""
 
-    def __init__(self, engine, rank: int, world: int, group=None):
+    def __init__(self, engine, rank: int, world: int, group=None, shard: str = "estimators"):
+        """``shard="estimators"`` (default): every estimator's context is built by one owner rank (module docstring).
+        ``shard="rows"``: the TRAIN ROWS of every estimator are split over the ranks (``_logits_rows``) — the mode for
+        fewer estimators than GPUs, where a single estimator's 50 000-row self-attention would otherwise run on one
+        GPU."""
         self.engine = engine
+        self.shard = shard
         self.model = engine.model
         self.rank, self.world, self.group = rank, world, group
         self.groups = engine.groups
@@ -159,7 +164,16 @@ class ShardedEngine:
                     self.subs.append(_Sub(gi, r, pos, [engine.groups[gi]["idx"][k] for k in pos]))
         self._gather = None
         self._comm = None
+        self._rows = None          # buffers of the row-sharded mode
         self.exchange = None       # filled per call: bytes gathered, for the bench line
+        if shard == "rows":
+            if not tabular:
+                raise ValueError("row sharding needs the bf16 path and tabular estimator groups")
+            # rows per rank: a multiple of the 48-key attention tile, so that key tiles never straddle two ranks and
+            # are exactly the tiles of the unsharded layout (bit-identical results)
+            self.seg_rows = -(-(-(-n_tr // world)) // 48) * 48
+            if (world - 1) * self.seg_rows >= n_tr:
+                raise ValueError(f"{n_tr} train rows are too few to shard over {world} ranks in tiles of 48")
 
     # ------------------------------------------------------------------------------------------------
     def stage(self, X_test_per_member, image_test):
@@ -175,6 +189,8 @@ class ShardedEngine:
         return self._gather
 
     def logits_staged(self, staged) -> torch.Tensor:
+        if self.shard == "rows":
+            return self._logits_rows(staged)
         if self.plan.mode == "broadcast":
             return self._logits_broadcast(staged)
         eng, m, plan = self.engine, self.model, self.plan
@@ -240,6 +256,84 @@ class ShardedEngine:
             if cuda:
                 torch.cuda.current_stream(dev).wait_event(events[l])
             m.layers_run(st2, stb2, tsegs, n_te, n_tr, l, l + 1)
+        out = [None] * len(self.members)
+        for g, v in zip(eng.groups, views2):
+            lg = m.decode(v[0])
+            for k, i in enumerate(g["idx"]):
+                out[i] = lg[k]
+        return torch.stack(out)
+
+    # ------------------------------------------------------------------------------------------------
+    def _logits_rows(self, staged) -> torch.Tensor:
+        """Row-sharded context build.  Rank r holds train rows [r * seg_rows, (r+1) * seg_rows) of EVERY estimator and
+        runs the row-wise sublayers (feature attention, projections, MLP, LayerNorms) on them alone.  For the item
+        attention each rank writes its rows' K / V^T planes into its chunk of two gather buffers, the buffers are
+        all-gathered (two ``all_gather_into_tensor`` per layer, in place), and the rank's query rows attend to all
+        keys through row-segmented tensor maps: no all-to-all, the state never leaves its rank.  The head-0 K/V blocks
+        every rank kept for its rows are all-gathered once after the last layer into the context the test pass reads
+        (again as row segments).  Work per rank: 1/W of everything; bit-identical to the unsharded engine."""
+        eng, m = self.engine, self.model
+        dev = m.device
+        W, r, L = self.world, self.rank, m.geom.nlayers
+        eng.nan_flag.zero_()
+        flag = eng.nan_flag
+        n_tr = eng.groups[0]["y_train"].shape[1]
+        seg = self.seg_rows
+        Sp = (seg + 63) // 64 * 64
+        lo, hi = r * seg, min((r + 1) * seg, n_tr)
+        S_loc = hi - lo
+        if self._rows is None:
+            bufs = []
+            for g, T in zip(eng.groups, self.Ts):
+                B = len(g["idx"])
+                chunk = B * T * 6 * Sp * 32 * 2                 # K (or V^T) planes of one rank's rows
+                block = 2 * B * T * Sp * 32 * 2                 # head-0 K0 + V0^T of one layer, one rank's rows
+                bufs.append(dict(kg=torch.zeros((W, chunk), dtype=torch.uint8, device=dev),
+                                 vtg=torch.zeros((W, chunk), dtype=torch.uint8, device=dev),
+                                 ctx=torch.zeros((W, L, block), dtype=torch.uint8, device=dev), chunk=chunk, block=block))
+            self._rows = bufs
+        bufs = self._rows
+        tok_tr = tok_te = None
+        if staged["img_test"] is not None:
+            tok_tr, tok_te = eng.train_image_tokens(), m.stem_image(staged["img_test"])
+        stats = [m.stem_tab_fit(torch.cat([g["X_train"], Xte], dim=1), n_tr)
+                 for g, Xte in zip(eng.groups, staged["X_test"])]
+        # ---- context build on this rank's rows of every estimator ---------------------------------------------
+        st, stb, views = m._group_buffers([(len(g["idx"]), S_loc, T) for g, T in zip(eng.groups, self.Ts)])
+        segs = []
+        for gi, (g, v) in enumerate(zip(eng.groups, views)):
+            ls, b = g["label_stats"], bufs[gi]
+            m.embed(g["X_train"][:, lo:hi].contiguous(), stats[gi], None if tok_tr is None else tok_tr[lo:hi].contiguous(),
+                    g["y_train"][:, lo:hi].contiguous(), ls[0], ls[1], m.positional_embeddings(self.Ts[gi] - 1),
+                    B=len(g["idx"]), S=S_loc, F=g["F"], x_bstride=S_loc * g["F"], y_bstride=S_loc, nan_flag=flag, out=v)
+            segs.append(dict(B=len(g["idx"]), T=self.Ts[gi], kv=b["ctx"][r, 0], layer_stride=b["block"], seg_rows=seg,
+                             kg=b["kg"], vtg=b["vtg"], gather_stride=b["chunk"], rank=r, n_ranks=W, n_rows_total=n_tr,
+                             bufs=b))
+        nbytes = 0
+        for l in range(L):
+            m.layers_run(st, stb, segs, S_loc, None, l, l + 1, phase=1)
+            for b in bufs:
+                dist.all_gather_into_tensor(b["kg"].view(-1), b["kg"][r] if dev.type == "cuda" else b["kg"][r].clone(), group=self.group)
+                dist.all_gather_into_tensor(b["vtg"].view(-1), b["vtg"][r] if dev.type == "cuda" else b["vtg"][r].clone(), group=self.group)
+                nbytes += 2 * (W - 1) * b["chunk"]
+            m.layers_run(st, stb, segs, S_loc, None, l, l + 1, phase=2)
+        for b in bufs:
+            dist.all_gather_into_tensor(b["ctx"].view(-1), b["ctx"][r].view(-1) if dev.type == "cuda" else b["ctx"][r].reshape(-1).clone(), group=self.group)
+            nbytes += (W - 1) * L * b["block"]
+        self.exchange = {"collective": "all_gather_into_tensor", "calls_per_step": 2 * L * len(bufs) + len(bufs),
+                         "bytes_received_per_rank": int(nbytes), "mode": "rows", "rows_per_rank": seg}
+        # ---- this rank's test rows against every estimator's gathered context ------------------------------------
+        n_te = staged["X_test"][0].shape[1]
+        y_nan = torch.full((1, n_te), float("nan"), dtype=torch.float32, device=dev)
+        st2, stb2, views2 = m._group_buffers([(len(g["idx"]), n_te, T) for g, T in zip(eng.groups, self.Ts)])
+        tsegs = []
+        for gi, (g, v) in enumerate(zip(eng.groups, views2)):
+            ls, b = g["label_stats"], bufs[gi]
+            m.embed(staged["X_test"][gi], stats[gi], tok_te, y_nan, ls[0], ls[1], m.positional_embeddings(self.Ts[gi] - 1),
+                    B=len(g["idx"]), S=n_te, F=g["F"], x_bstride=n_te * g["F"], y_bstride=0, nan_flag=flag, out=v)
+            tsegs.append(dict(B=len(g["idx"]), T=self.Ts[gi], kv=b["ctx"][0, 0], layer_stride=b["block"], seg_rows=seg,
+                              rank_stride=L * b["block"], bufs=b, n_ranks=W))
+        m.layers_run(st2, stb2, tsegs, n_te, n_tr, 0, L)
         out = [None] * len(self.members)
         for g, v in zip(eng.groups, views2):
             lg = m.decode(v[0])

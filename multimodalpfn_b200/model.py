@@ -250,22 +250,34 @@ class B200PerFeatureTransformer:
                                                         n_train, kvp, ws.data_ptr(), nbytes, self._stream()),
                        "mmpfn_layers_test_multi")
 
-    def layers_run(self, state, state_b, segs, S: int, n_train: Optional[int], layer_begin: int, layer_end: int):
+    def layers_run(self, state, state_b, segs, S: int, n_train: Optional[int], layer_begin: int, layer_end: int,
+                   phase: int = 0):
         """Layers ``[layer_begin, layer_end)`` over segment states held back to back in ``state`` / ``state_b``
         (``_group_buffers``), with the K/V context of every segment addressed explicitly (``mmpfn_layers_run``).
         ``segs``: dicts ``B, T, kv`` (uint8 tensor view starting at the segment's block of layer 0),
         ``layer_stride`` / ``rank_stride`` (bytes) and ``slots``.  ``n_train=None``: train pass (writes the K/V),
         else test pass against ``n_train`` context rows."""
         n = len(segs)
-        arr = (_lib.KvSegment * n)(*[_lib.KvSegment(int(s["B"]), int(s["T"]), s["kv"].data_ptr(), int(s.get("layer_stride", 0)),
-                                                    int(s.get("slots", 0)), 0, int(s.get("rank_stride", 0))) for s in segs])
+        def seg(s):
+            k = _lib.KvSegment()
+            k.B, k.T, k.kv = int(s["B"]), int(s["T"]), s["kv"].data_ptr()
+            k.layer_stride, k.slots, k.rank_stride = int(s.get("layer_stride", 0)), int(s.get("slots", 0)), int(s.get("rank_stride", 0))
+            k.seg_rows = int(s.get("seg_rows", 0))
+            if s.get("kg") is not None:        # row-sharded context build (dist.py "rows" mode; include/mmpfn_b200.h)
+                k.kg, k.vtg = s["kg"].data_ptr(), s["vtg"].data_ptr()
+                k.gather_stride, k.rank, k.n_ranks = int(s["gather_stride"]), int(s["rank"]), int(s["n_ranks"])
+                k.n_rows_total = int(s["n_rows_total"])
+            return k
+        arr = (_lib.KvSegment * n)(*[seg(s) for s in segs])
         plain = (_lib.Segment * n)(*[_lib.Segment(int(s["B"]), int(s["T"])) for s in segs])
-        nbytes = self.lib.mmpfn_layers_multi_ws_bytes(self._g, plain, n, S)
+        S_alloc = max([S] + [int(s.get("seg_rows", 0)) for s in segs]) if n_train is None else S
+        nbytes = self.lib.mmpfn_layers_multi_ws_bytes(self._g, plain, n, S_alloc)
         ws = self._scratch("layers", nbytes)
         _lib.check(self.lib.mmpfn_layers_run(self._g, self._w if n_train is None else self._w_test, state.data_ptr(),
                                              state_b.data_ptr(), arr, n, S,
                                              0 if n_train is None else int(n_train), 1 if n_train is None else 0,
-                                             int(layer_begin), int(layer_end), ws.data_ptr(), nbytes, self._stream()),
+                                             int(layer_begin), int(layer_end), int(phase), ws.data_ptr(), nbytes,
+                                             self._stream()),
                    "mmpfn_layers_run")
 
     def alloc_kv(self, B: int, n_train: int, T: int) -> torch.Tensor:

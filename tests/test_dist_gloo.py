@@ -118,18 +118,35 @@ class FakeModel:
         state[:, :, T - 1, :] += yy.expand(B, S)[..., None]
         return state, None
 
-    def layers_run(self, state, state_b, segs, S, n_train, l0, l1):
+    def layers_run(self, state, state_b, segs, S, n_train, l0, l1, phase=0):
         off = 0
         for sg in segs:
             B, T = sg["B"], sg["T"]
             st = state[off:off + B * S * T].view(B, S, T, E)
             off += B * S * T
-            flat = sg["kv_buffer"].view(-1)
+            rows = sg.get("bufs")                       # row-sharded mode (dist.py "rows"): buffers by rank
+            flat = None if rows is not None else sg["kv_buffer"].view(-1)
             for l in range(l0, l1):
-                if n_train is None:                     # train: write this layer's block [B][T] float64
+                if n_train is None and rows is not None:
+                    # train rows sharded: phase 1 leaves this rank's partial row sum in its gather chunk and its
+                    # context block; phase 2 (after the caller's all-gather) moves the state on with the total
+                    r = sg["rank"]
+                    if phase != 2:
+                        part = st[..., 0].sum(1).double()
+                        rows["kg"][r][:B * T * 8].view(torch.float64).view(B, T)[:] = part
+                        rows["ctx"][r, l][:B * T * 8].view(torch.float64).view(B, T)[:] = part + (l if r == 0 else 0)
+                    if phase != 1:
+                        tot = sum(rows["kg"][k][:B * T * 8].view(torch.float64).view(B, T) for k in range(sg["n_ranks"]))
+                        st.mul_(0.5).add_(1.0).add_((tot.float() * 1e-4)[:, None, :, None])
+                elif n_train is None:                   # train: write this layer's block [B][T] float64
                     a = sg["kv_offset"] + l * (sg["layer_stride"] or B * T * 8)
-                    flat[a:a + B * T * 8].view(torch.float64).view(B, T)[:] = st[..., 0].sum(1).double() + l
-                    st.mul_(0.5).add_(1.0)
+                    tot = st[..., 0].sum(1).double()
+                    flat[a:a + B * T * 8].view(torch.float64).view(B, T)[:] = tot + l
+                    st.mul_(0.5).add_(1.0).add_((tot.float() * 1e-4)[:, None, :, None])
+                elif rows is not None:                  # test against a row-sharded context: the chunks add up
+                    for b in range(B):
+                        ctx = sum(rows["ctx"][k, l][b * T * 8:(b + 1) * T * 8].view(torch.float64) for k in range(sg["n_ranks"]))
+                        st[b] = st[b] * 0.5 + (ctx.float() * 1e-3)[None, :, None]
                 else:                                   # test: read estimator b at (rank, slot)
                     c = sg["slots"] or B
                     for b in range(B):
@@ -173,15 +190,15 @@ class FakeModel:
         return self.decode(views[0][0])
 
 
-def _make_engine(rank_seed, n_a=4, n_b=4):
+def _make_engine(rank_seed, n_a=4, n_b=4, n_train=20):
     from multimodalpfn_b200.engine import B200InferenceEngine
     rng = np.random.default_rng(0)
     members = []
     for e in range(n_a + n_b):
         F = 6 if e < n_a else 4
-        members.append(dict(X_train=rng.standard_normal((20, F)).astype(np.float32),
-                            y_train=rng.integers(0, 3, 20).astype(np.float32), class_perm=None))
-    img_train = rng.standard_normal((20, 1, 8)).astype(np.float32)
+        members.append(dict(X_train=rng.standard_normal((n_train, F)).astype(np.float32),
+                            y_train=rng.integers(0, 3, n_train).astype(np.float32), class_perm=None))
+    img_train = rng.standard_normal((n_train, 1, 8)).astype(np.float32)
     eng = B200InferenceEngine(FakeModel(), members, img_train)
     rng2 = np.random.default_rng(10 + rank_seed)
     X_tests = [rng2.standard_normal((5, m["X_train"].shape[1])).astype(np.float32) for m in members]
@@ -189,33 +206,33 @@ def _make_engine(rank_seed, n_a=4, n_b=4):
     return eng, X_tests, img_test
 
 
-def _worker(rank, world, port, q, n_a, n_b):
+def _worker(rank, world, port, q, n_a, n_b, shard="estimators", n_train=20):
     os.environ["MASTER_ADDR"] = "127.0.0.1"
     os.environ["MASTER_PORT"] = str(port)
     dist.init_process_group("gloo", rank=rank, world_size=world)
     try:
-        eng, X_tests, img_test = _make_engine(rank, n_a, n_b)
+        eng, X_tests, img_test = _make_engine(rank, n_a, n_b, n_train)
         ref = eng.logits(X_tests, img_test, graph=False)          # unsharded, this rank's chunk
-        sh = ShardedEngine(eng, rank, world)
+        sh = ShardedEngine(eng, rank, world, shard=shard)
         got = sh.logits(X_tests, img_test)
         got2 = sh.logits(X_tests, img_test)                       # the gather buffer is reused across calls
         ok = bool(torch.allclose(got, ref, rtol=0, atol=1e-4)) and bool(torch.equal(got, got2))
         rows = all_gather_rows(got[0, :, :3].contiguous())
         ok2 = rows.shape == (world * 5, 3) and torch.equal(rows[rank * 5:(rank + 1) * 5], got[0, :, :3])
         owned = sorted(i for s in sh.subs if s.owner == rank for i in s.members)
-        q.put((rank, ok, ok2, owned, sh.plan.mode, float((got - ref).abs().max())))
+        q.put((rank, ok, ok2, owned, sh.exchange["mode"], float((got - ref).abs().max())))
     finally:
         dist.destroy_process_group()
 
 
-def _run(world, n_a=4, n_b=4):
+def _run(world, n_a=4, n_b=4, shard="estimators", n_train=20):
     s = socket.socket()
     s.bind(("127.0.0.1", 0))
     port = s.getsockname()[1]
     s.close()
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
-    procs = [ctx.Process(target=_worker, args=(r, world, port, q, n_a, n_b)) for r in range(world)]
+    procs = [ctx.Process(target=_worker, args=(r, world, port, q, n_a, n_b, shard, n_train)) for r in range(world)]
     for p in procs:
         p.start()
     res = sorted(q.get(timeout=180) for _ in procs)
@@ -245,3 +262,21 @@ def test_sharded_engine_world2_broadcast_fallback():
     assert all(r[1] and r[2] for r in res), res
     assert all(r[4] == "broadcast" for r in res)
     assert sorted(res[0][3] + res[1][3]) == list(range(5))
+
+
+def test_sharded_engine_world2_rows():
+    """Train rows split over the ranks (96 + 4 of 100 rows: the last rank's segment is ragged)."""
+    res = _run(2, n_a=2, n_b=1, shard="rows", n_train=100)
+    assert all(r[1] and r[2] for r in res), res
+    assert all(r[4] == "rows" for r in res)
+
+
+def test_sharded_engine_world4_rows_single_estimator():
+    res = _run(4, n_a=1, n_b=0, shard="rows", n_train=190)            # 48 + 48 + 48 + 46 rows of ONE estimator
+    assert all(r[1] and r[2] for r in res), res
+
+
+def test_rows_mode_rejects_short_tables():
+    eng, _, _ = _make_engine(0, 1, 0, n_train=96)
+    with pytest.raises(ValueError, match="too few"):
+        ShardedEngine(eng, 0, 4, shard="rows")

@@ -35,5 +35,28 @@ for precision in ("bf16", "fp32"):
           f"repeat equal = {bool(torch.equal(got, got2))}; gather ok = {bool(ok)}; exchange = {sh.exchange}", flush=True)
     assert err == 0.0 if sh.plan.mode != "broadcast" and precision == "bf16" else err < 1e-4, err
     assert ok and torch.equal(got, got2)
+
+# ---- train rows sharded over the ranks (shard="rows"): bit-identical to the unsharded engine as well ----------------
+name, n_est = ("pad_ufes", 8) if world <= 4 else ("img_text_10k", 2)
+d = make_dataset(name, 0)
+n_te = 120
+Xte = d["X_test"][rng.permutation(len(d["X_test"]))[:n_te]]
+img = rng.standard_normal((n_te,) + d["img_test"].shape[1:]).astype(np.float32)
+for n_members in (n_est, 1):
+    clf = MMPFNClassifier(mixer_type="MGM+CAP", mgm_heads=2, cap_heads=4, n_estimators=n_members, model_path=(sd, geom),
+                          device=f"cuda:{local}", inference_precision="bf16", ignore_pretraining_limits=True,
+                          random_state=0).fit(d["X_train"], d["img_train"], d["y_train"])
+    X_tests = [m.transform(Xte) for m in clf.members_]
+    ref = clf.executor_.logits(X_tests, img, graph=False).clone()
+    sh = ShardedEngine(clf.executor_, rank, world, shard="rows")
+    got = sh.logits(X_tests, img).clone()
+    got2 = sh.logits(X_tests, img)
+    err = (got - ref).abs().max().item()
+    print(f"rank {rank}/{world} rows mode, {name}, {n_members} estimator(s), {sh.seg_rows} rows per rank: "
+          f"max |sharded - unsharded| logits = {err:.3e}; repeat equal = {bool(torch.equal(got, got2))}; "
+          f"exchange = {sh.exchange}", flush=True)
+    assert err == 0.0 and torch.equal(got, got2), err
+    del clf, sh
+    torch.cuda.empty_cache()
 dist.barrier()
 dist.destroy_process_group()

@@ -59,7 +59,7 @@ def emit(**kw):
         print(json.dumps(kw), flush=True)
 
 
-def run_table(name, dataset, steps):
+def run_table(name, dataset, steps, n_est=N_EST, shard="estimators"):
     d = make_dataset(dataset, 0)
     n_tr, n_te_all = len(d["y_train"]), len(d["y_test"])
     per = n_te_all // world
@@ -67,7 +67,7 @@ def run_table(name, dataset, steps):
     X_test = d["X_test"][sl]
     img_test = None if d["img_test"] is None else d["img_test"][sl]
     t0 = time.perf_counter()
-    clf = MMPFNClassifier(mixer_type="MGM+CAP", mgm_heads=8, cap_heads=8, features_per_group=2, n_estimators=N_EST,
+    clf = MMPFNClassifier(mixer_type="MGM+CAP", mgm_heads=8, cap_heads=8, features_per_group=2, n_estimators=n_est,
                           model_path=(sd, geom), device=f"cuda:{local}", inference_precision="bf16",
                           ignore_pretraining_limits=True, random_state=0)
     clf.fit(d["X_train"], d["img_train"], d["y_train"])
@@ -75,7 +75,7 @@ def run_table(name, dataset, steps):
     eng = clf.executor_
     if world > 1:
         from multimodalpfn_b200.dist import ShardedEngine
-        eng = ShardedEngine(eng, rank, world)
+        eng = ShardedEngine(eng, rank, world, shard=shard)
         clf.executor_ = eng
     H_img = 0 if d["img_train"] is None else 8
     Ts = sorted({(g["F"] + 1) // 2 + H_img + 1 for g in eng.groups}, reverse=True)
@@ -120,7 +120,7 @@ def run_table(name, dataset, steps):
     e2e = rmax(time.perf_counter() - t0)
     emit(config=name, n_gpus=world, workload=f"{dataset}: {n_tr} train / {per * world} test rows ({per} per rank), "
          f"{d['X_train'].shape[1]} features" + ("" if d["img_train"] is None else f" + {d['img_train'].shape[1]} x 768-d embeddings")
-         + f", {N_EST} estimators, bf16, context rebuilt per call", T=Ts, ms_per_step=ms, value=per * world / ms * 1e3,
+         + f", {n_est} estimator(s), bf16, context rebuilt per call, sharding: {shard}", T=Ts, ms_per_step=ms, value=per * world / ms * 1e3,
          unit="test rows/s", e2e_ms=e2e * 1e3, e2e_value=per * world / e2e, host_transform_ms_per_rank=t_host * 1e3,
          fit_s=t_fit, algorithmic_tflop=fl / 1e12, achieved_tflops_per_gpu=fl / (ms * 1e-3) / 1e12 / world,
          exchange=getattr(eng, "exchange", None), peak_mem_gib=torch.cuda.max_memory_allocated() / 2**30,
@@ -166,6 +166,12 @@ for cfg in (sys.argv[1:] or ["cfg3"]):
         run_table("cfg3", "img_text_10k", steps=2)
     elif cfg == "cfg4":
         run_table("cfg4", "large_ctx_50k", steps=2)
+    elif cfg == "cfg4_rows":        # the same table with the TRAIN ROWS of every estimator split over the ranks
+        run_table("cfg4_rows", "large_ctx_50k", steps=2, shard="rows")
+    elif cfg == "cfg4_one":         # ONE estimator's 50 000-row context: estimator ownership leaves W - 1 GPUs idle
+        run_table("cfg4_one", "large_ctx_50k", steps=2, n_est=1)
+    elif cfg == "cfg4_one_rows":    # ... row sharding uses all of them
+        run_table("cfg4_one_rows", "large_ctx_50k", steps=2, n_est=1, shard="rows")
     elif cfg == "cfg5":
         run_tasks(256, steps=2)
     elif cfg == "dry":              # small stand-ins that exercise the same code paths (script check before a long run)
