@@ -5,7 +5,11 @@
 
 Times, with CUDA events around the eager device-resident step: (a) the engine's one-pass-over-all-groups path,
 (b) group after group on one stream, (c) the groups on two streams (two model objects: private scratch each),
-(d) as (c) with the narrower group on a high-priority stream.  Logits must be bit-identical in all of them."""
+(d) as (c) with the narrower group on a high-priority stream.  (b)-(d) use the same model objects (each draws its own
+positional noise, so they are compared with each other, not with (a)).
+
+Measured (B200, profiles/r02_overlap_probe.txt): 31.88 / 33.35 / 31.38 / 32.12 ms — both kernels families fill all
+148 SMs, so there is nothing to overlap; the one-pass path stays."""
 import os
 import sys
 
@@ -39,7 +43,7 @@ def group_pass(m, g, Xte, tok_tr, tok_te):
 
 def serial():
     tok_tr, tok_te = eng.train_image_tokens(), eng.model.stem_image(staged["img_test"])
-    return [group_pass(eng.model, g, Xte, tok_tr, tok_te) for g, Xte in zip(eng.groups, staged["X_test"])]
+    return [group_pass(m, g, Xte, tok_tr, tok_te) for m, g, Xte in zip(models, eng.groups, staged["X_test"])]
 
 
 def streams(prio):
@@ -85,8 +89,7 @@ order = [i for g in eng.groups for i in g["idx"]]
 t_serial, o1 = timed(serial)
 t_par, o2 = timed(lambda: streams(False))
 t_prio, o3 = timed(lambda: streams(True))
-for name, o in (("serial", o1), ("two streams", o2), ("two streams, priority", o3)):
-    got = torch.cat(o)
-    print(name, "bit-identical to the one-pass path:", bool(torch.equal(got, ref[order])))
+for name, o in (("two streams", o2), ("two streams, priority", o3)):
+    print(name, "bit-identical to group after group:", bool(torch.equal(torch.cat(o), torch.cat(o1))))
 print(f"one pass over all groups {t_multi:.2f} ms | group after group {t_serial:.2f} ms | two streams {t_par:.2f} ms | "
       f"two streams, narrow group high priority {t_prio:.2f} ms")
