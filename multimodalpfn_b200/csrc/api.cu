@@ -413,17 +413,25 @@ static int check_layers_args(const mmpfn_geometry* g, const mmpfn_weights* w, fl
   return MMPFN_OK;
 }
 
+static int layers_run(const mmpfn_geometry* g, const mmpfn_weights* w, float* state, uint16_t* state_b,
+                      const mmpfn_kv_segment* ks, int n_seg, int S, int n_train, int train, int layer_begin,
+                      int layer_end, int phase, void* workspace, size_t workspace_bytes, cudaStream_t st);
+
 int mmpfn_layers_train(const mmpfn_geometry* g, const mmpfn_weights* w, float* state, uint16_t* state_b, int B, int S,
                        int T, int precision, void* kv, void* workspace, size_t workspace_bytes, void* stream) {
   LayerWs ws;
   MMPFN_TRY(check_layers_args(g, w, state, state_b, B, S, T, precision, workspace, workspace_bytes, &ws));
   cudaStream_t st = (cudaStream_t)stream;
+  if (precision == MMPFN_BF16) {      // one segment of the general bf16 pass (same workspace layout)
+    mmpfn_kv_segment k{};
+    k.B = B; k.T = T; k.kv = kv;
+    return layers_run(g, w, state, state_b, &k, 1, S, 0, 1, 0, g->nlayers, 0, workspace, workspace_bytes, st);
+  }
   const long long M = (long long)B * S * T;
-  const int Sp = kv_pad(S);
   for (int l = 0; l < g->nlayers; ++l) {
     const LayerW lw = layer_w(w, l);
     MMPFN_TRY(feature_attention(lw, state, state_b, M, (long long)B * S, T, precision, ws, st));
-    if (precision == MMPFN_F32) {
+    {
       MMPFN_TRY(launch_sgemm(gemm(state, kE, lw.iqkv, kE, nullptr, ws.qkv, 3 * kE, (int)M, 3 * kE, kE), EPI_NONE, st));
       if (kv) {
         float* kvl = (float*)kv + (size_t)l * B * T * S * 2 * kD;
@@ -436,20 +444,6 @@ int mmpfn_layers_train(const mmpfn_geometry* g, const mmpfn_weights* w, float* s
       a.o_outer = (long long)S * T * kE; a.o_inner = kE; a.o_row = (long long)T * kE;
       a.planes = B * T; a.inner = T; a.n_q = S; a.n_kv = S; a.shared_kv = 0;
       MMPFN_TRY(launch_item_attn_f32(a, st));
-    } else {
-      TcGemm q{};
-      q.A = state_b; q.W = lw.iqkv_b; q.N = 3 * kE; q.K = kE; q.items = 1; q.B = B; q.S = S; q.T = T;
-      q.epi = TC_EPI_QKV_ITEMS; q.q_out = ws.qi; q.k_out = ws.ki; q.vt_out = ws.vti; q.S_pad = Sp;
-      if (kv) {
-        uint16_t* kvl = (uint16_t*)kv + (size_t)l * B * T * Sp * 2 * kD;
-        q.k0_out = kvl;
-        q.vt0_out = kvl + (size_t)B * T * Sp * kD;
-      }
-      MMPFN_TRY(proj_gemm(q, st));
-      TcItemAttn a{};
-      a.q = ws.qi; a.k = ws.ki; a.vt = ws.vti; a.out = ws.att_b;
-      a.B = B; a.T = T; a.n_q = S; a.Sq_pad = Sp; a.n_kv = S; a.Skv_pad = Sp; a.shared_kv = 0;
-      MMPFN_TRY(launch_tc_item_attn(a, st));
     }
     MMPFN_TRY(out_proj_ln(lw, state, state_b, M, precision, ws, st));
     MMPFN_TRY(mlp(lw, state, state_b, M, precision, ws, st));
@@ -464,12 +458,16 @@ int mmpfn_layers_test(const mmpfn_geometry* g, const mmpfn_weights* w, float* st
   MMPFN_TRY(check_layers_args(g, w, state, state_b, B, S, T, precision, workspace, workspace_bytes, &ws));
   if (!kv || n_train < 1) { set_error("layers_test: needs the K/V context of the train rows"); return MMPFN_EINVAL; }
   cudaStream_t st = (cudaStream_t)stream;
+  if (precision == MMPFN_BF16) {
+    mmpfn_kv_segment k{};
+    k.B = B; k.T = T; k.kv = const_cast<void*>(kv);
+    return layers_run(g, w, state, state_b, &k, 1, S, n_train, 0, 0, g->nlayers, 0, workspace, workspace_bytes, st);
+  }
   const long long M = (long long)B * S * T;
-  const int Sp = kv_pad(S), Np = kv_pad(n_train);
   for (int l = 0; l < g->nlayers; ++l) {
     const LayerW lw = layer_w(w, l);
     MMPFN_TRY(feature_attention(lw, state, state_b, M, (long long)B * S, T, precision, ws, st));
-    if (precision == MMPFN_F32) {
+    {
       // queries only (multi_head_attention.py:432-434); K/V come from the context
       MMPFN_TRY(launch_sgemm(gemm(state, kE, lw.iqkv, kE, nullptr, ws.qkv, kE, (int)M, kE, kE), EPI_NONE, st));
       const float* kvl = (const float*)kv + (size_t)l * B * T * n_train * 2 * kD;
@@ -480,16 +478,6 @@ int mmpfn_layers_test(const mmpfn_geometry* g, const mmpfn_weights* w, float* st
       a.o_outer = (long long)S * T * kE; a.o_inner = kE; a.o_row = (long long)T * kE;
       a.planes = B * T; a.inner = T; a.n_q = S; a.n_kv = n_train; a.shared_kv = 1;
       MMPFN_TRY(launch_item_attn_f32(a, st));
-    } else {
-      TcGemm q{};
-      q.A = state_b; q.W = lw.iqkv_b; q.N = kE; q.K = kE; q.items = 1; q.B = B; q.S = S; q.T = T;
-      q.epi = TC_EPI_QKV_ITEMS; q.q_out = ws.qi; q.S_pad = Sp;
-      MMPFN_TRY(proj_gemm(q, st));
-      const uint16_t* kvl = (const uint16_t*)kv + (size_t)l * B * T * Np * 2 * kD;
-      TcItemAttn a{};
-      a.q = ws.qi; a.k = kvl; a.vt = kvl + (size_t)B * T * Np * kD; a.out = ws.att_b;
-      a.B = B; a.T = T; a.n_q = S; a.Sq_pad = Sp; a.n_kv = n_train; a.Skv_pad = Np; a.shared_kv = 1;
-      MMPFN_TRY(launch_tc_item_attn(a, st));
     }
     MMPFN_TRY(out_proj_ln(lw, state, state_b, M, precision, ws, st));
     MMPFN_TRY(mlp(lw, state, state_b, M, precision, ws, st));
@@ -585,10 +573,48 @@ static int layers_run(const mmpfn_geometry* g, const mmpfn_weights* w, float* st
   const int Sp = kv_pad(Sa), Np = kv_pad(n_train);
   LayerWs flat{};
   flat.hid_b = ws.hid_b; flat.qkv_b = ws.hid_b; flat.att_b = ws.att_b;
+  // Chunked (L2-resident) schedule of the row-wise sublayers: pays once the token axis is several times the L2.
+  // Chunk sizes are whole rounds of 128-token tiles over the SMs (2 rounds for the feature chain, whose qkv block
+  // is the large one; 3 for out-projection -> MLP).  Results do not depend on it (every kernel works row by row).
+  long long chunk_feat = 0, chunk_mlp = 0;
+  {
+    // (a round = 128-token tiles for all SMs; the QKV projection splits the SMs three ways over its 576 outputs)
+    const long long round = (long long)(device_sm_count() / 3 * 3) * 128;
+    long long cf = 2 * round, cm = 3 * round;
+#ifdef MMPFN_DEBUG
+    if (const char* e = getenv("MMPFN_CHUNK_FEAT")) cf = atoll(e) * round;
+    if (const char* e = getenv("MMPFN_CHUNK_MLP")) cm = atoll(e) * round;
+#endif
+    if (cf > 0 && M >= 3 * cf) chunk_feat = cf;
+    if (cm > 0 && M >= 2 * cm) chunk_mlp = cm;
+  }
   for (int l = layer_begin; l < layer_end; ++l) {
     const LayerW lw = layer_w(w, l);
     // features: QKV over all tokens, attention per segment (rows of T_i tokens), out-projection + LN over all
-    if (phase != 2) {
+    if (phase != 2 && chunk_feat > 0) {
+      // L2-resident schedule: QKV -> attention -> out-projection + LayerNorm run chunk by chunk of whole table rows, so
+      // that the qkv block (1 152 B per token) and the attention output (384 B) of a chunk are written and read back
+      // while they sit in the 126 MB L2 and are overwritten there by the next chunk: HBM sees the state once
+      long long off = 0;
+      for (int i = 0; i < n_seg; ++i) {
+        const int T = segs[i].T;
+        const long long rows = (long long)segs[i].B * S;
+        const long long R = chunk_feat / T > 0 ? chunk_feat / T : 1;
+        for (long long r0 = 0; r0 < rows; r0 += R) {
+          const long long n = rows - r0 < R ? rows - r0 : R, t0 = off + r0 * T;
+          TcGemm a{};
+          a.A = state_b + t0 * kE; a.W = lw.fqkv_b; a.M = (int)(n * T); a.N = 3 * kE; a.K = kE; a.epi = TC_EPI_BF16;
+          a.out_bf16 = ws.hid_b;
+          MMPFN_TRY(proj_gemm(a, st));
+          MMPFN_TRY(launch_feat_attn_bf16(ws.hid_b, ws.att_b, n, T, st));
+          TcGemm o{};
+          o.A = ws.att_b; o.W = lw.fout_b; o.M = (int)(n * T); o.N = kE; o.K = kE; o.epi = TC_EPI_RESID_LN;
+          o.resid_f32 = state + t0 * kE; o.ln_bf16 = state_b + t0 * kE;
+          MMPFN_TRY(proj_gemm(o, st));
+        }
+        off += rows * T;
+      }
+    } else if (phase != 2) {
       TcGemm a{};
       a.A = state_b; a.W = lw.fqkv_b; a.M = (int)M; a.N = 3 * kE; a.K = kE; a.epi = TC_EPI_BF16; a.out_bf16 = ws.hid_b;
       MMPFN_TRY(proj_gemm(a, st));
@@ -656,9 +682,20 @@ static int layers_run(const mmpfn_geometry* g, const mmpfn_weights* w, float* st
         if (phase != 1) MMPFN_TRY(launch_tc_item_attn(a, st));
         off += (long long)B * S * T;
       }
-      if (phase != 1) MMPFN_TRY(out_proj_ln(lw, state, state_b, M, MMPFN_BF16, flat, st));
+      if (phase != 1 && chunk_mlp == 0) MMPFN_TRY(out_proj_ln(lw, state, state_b, M, MMPFN_BF16, flat, st));
     }
-    if (phase != 1) MMPFN_TRY(mlp(lw, state, state_b, M, MMPFN_BF16, flat, st));
+    if (phase != 1 && chunk_mlp == 0) MMPFN_TRY(mlp(lw, state, state_b, M, MMPFN_BF16, flat, st));
+    if (phase != 1 && chunk_mlp > 0) {
+      // out-projection + LayerNorm, then the MLP sublayer, chunk by chunk of the flat token axis: the state the first
+      // writes (1 152 B per token) is read — and overwritten in place — by the second while it is still in L2
+      for (long long t0 = 0; t0 < M; t0 += chunk_mlp) {
+        const long long m = M - t0 < chunk_mlp ? M - t0 : chunk_mlp;
+        LayerWs part = flat;
+        part.att_b = ws.att_b + t0 * kE;
+        MMPFN_TRY(out_proj_ln(lw, state + t0 * kE, state_b + t0 * kE, m, MMPFN_BF16, part, st));
+        MMPFN_TRY(mlp(lw, state + t0 * kE, state_b + t0 * kE, m, MMPFN_BF16, part, st));
+      }
+    }
   }
   return MMPFN_OK;
 }

@@ -211,6 +211,32 @@ def test_multi_group_pass_equals_per_group(fit_mode):
     assert torch.isfinite(a).all() and torch.equal(a, b)
 
 
+def test_chunked_schedule_equals_one_estimator_at_a_time():
+    """At 2 000 train rows x 8 estimators the row-wise sublayers run chunk by chunk of the token axis (L2-resident
+    schedule, csrc/api.cu layers_run); one estimator alone stays below the chunking threshold.  Every kernel works
+    row by row, so the logits must be identical bit for bit."""
+    from multimodalpfn_b200.classifier import MMPFNClassifier
+    from multimodalpfn_b200.engine import B200InferenceEngine
+    from multimodalpfn_b200.preprocessing import transform_all
+    from multimodalpfn_b200.synth import Geometry, make_dataset, make_state_dict
+    geom = Geometry(mgm_heads=2, cap_heads=4)
+    sd = make_state_dict(geom, seed=3)
+    d = make_dataset("pad_ufes", 0)
+    clf = MMPFNClassifier(mixer_type="MGM+CAP", mgm_heads=2, cap_heads=4, features_per_group=2, n_estimators=8,
+                          model_path=(sd, geom), device="cuda", inference_precision="bf16",
+                          ignore_pretraining_limits=True, random_state=0)
+    clf.fit(d["X_train"], d["img_train"], d["y_train"])
+    eng = clf.executor_
+    X_tests = transform_all(clf.members_, d["X_test"][:100])
+    img = d["img_test"][:100]
+    all8 = eng.logits_staged(eng.stage(X_tests, img)).clone()
+    assert torch.isfinite(all8).all()
+    for i in (0, 3, 7):
+        one = B200InferenceEngine(eng.model, [eng.members[i]], eng.image_train)
+        lg = one.logits_staged(one.stage([X_tests[i]], img))
+        assert torch.equal(lg[0], all8[i]), i
+
+
 def test_graph_replay_survives_scratch_growth():
     """CUDA graphs hold raw pointers into the model's shared scratch buffers; a later, larger call replaces those
     buffers.  Sizes 120 -> 360 -> 120 test rows through the graphed path must each equal the eager path, and the
