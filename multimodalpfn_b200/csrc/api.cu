@@ -573,48 +573,10 @@ static int layers_run(const mmpfn_geometry* g, const mmpfn_weights* w, float* st
   const int Sp = kv_pad(Sa), Np = kv_pad(n_train);
   LayerWs flat{};
   flat.hid_b = ws.hid_b; flat.qkv_b = ws.hid_b; flat.att_b = ws.att_b;
-  // Chunked (L2-resident) schedule of the row-wise sublayers: pays once the token axis is several times the L2.
-  // Chunk sizes are whole rounds of 128-token tiles over the SMs (2 rounds for the feature chain, whose qkv block
-  // is the large one; 3 for out-projection -> MLP).  Results do not depend on it (every kernel works row by row).
-  long long chunk_feat = 0, chunk_mlp = 0;
-  {
-    // (a round = 128-token tiles for all SMs; the QKV projection splits the SMs three ways over its 576 outputs)
-    const long long round = (long long)(device_sm_count() / 3 * 3) * 128;
-    long long cf = 2 * round, cm = 3 * round;
-#ifdef MMPFN_DEBUG
-    if (const char* e = getenv("MMPFN_CHUNK_FEAT")) cf = atoll(e) * round;
-    if (const char* e = getenv("MMPFN_CHUNK_MLP")) cm = atoll(e) * round;
-#endif
-    if (cf > 0 && M >= 3 * cf) chunk_feat = cf;
-    if (cm > 0 && M >= 2 * cm) chunk_mlp = cm;
-  }
   for (int l = layer_begin; l < layer_end; ++l) {
     const LayerW lw = layer_w(w, l);
     // features: QKV over all tokens, attention per segment (rows of T_i tokens), out-projection + LN over all
-    if (phase != 2 && chunk_feat > 0) {
-      // L2-resident schedule: QKV -> attention -> out-projection + LayerNorm run chunk by chunk of whole table rows, so
-      // that the qkv block (1 152 B per token) and the attention output (384 B) of a chunk are written and read back
-      // while they sit in the 126 MB L2 and are overwritten there by the next chunk: HBM sees the state once
-      long long off = 0;
-      for (int i = 0; i < n_seg; ++i) {
-        const int T = segs[i].T;
-        const long long rows = (long long)segs[i].B * S;
-        const long long R = chunk_feat / T > 0 ? chunk_feat / T : 1;
-        for (long long r0 = 0; r0 < rows; r0 += R) {
-          const long long n = rows - r0 < R ? rows - r0 : R, t0 = off + r0 * T;
-          TcGemm a{};
-          a.A = state_b + t0 * kE; a.W = lw.fqkv_b; a.M = (int)(n * T); a.N = 3 * kE; a.K = kE; a.epi = TC_EPI_BF16;
-          a.out_bf16 = ws.hid_b;
-          MMPFN_TRY(proj_gemm(a, st));
-          MMPFN_TRY(launch_feat_attn_bf16(ws.hid_b, ws.att_b, n, T, st));
-          TcGemm o{};
-          o.A = ws.att_b; o.W = lw.fout_b; o.M = (int)(n * T); o.N = kE; o.K = kE; o.epi = TC_EPI_RESID_LN;
-          o.resid_f32 = state + t0 * kE; o.ln_bf16 = state_b + t0 * kE;
-          MMPFN_TRY(proj_gemm(o, st));
-        }
-        off += rows * T;
-      }
-    } else if (phase != 2) {
+    if (phase != 2) {
       TcGemm a{};
       a.A = state_b; a.W = lw.fqkv_b; a.M = (int)M; a.N = 3 * kE; a.K = kE; a.epi = TC_EPI_BF16; a.out_bf16 = ws.hid_b;
       MMPFN_TRY(proj_gemm(a, st));
@@ -682,20 +644,9 @@ static int layers_run(const mmpfn_geometry* g, const mmpfn_weights* w, float* st
         if (phase != 1) MMPFN_TRY(launch_tc_item_attn(a, st));
         off += (long long)B * S * T;
       }
-      if (phase != 1 && chunk_mlp == 0) MMPFN_TRY(out_proj_ln(lw, state, state_b, M, MMPFN_BF16, flat, st));
+      if (phase != 1) MMPFN_TRY(out_proj_ln(lw, state, state_b, M, MMPFN_BF16, flat, st));
     }
-    if (phase != 1 && chunk_mlp == 0) MMPFN_TRY(mlp(lw, state, state_b, M, MMPFN_BF16, flat, st));
-    if (phase != 1 && chunk_mlp > 0) {
-      // out-projection + LayerNorm, then the MLP sublayer, chunk by chunk of the flat token axis: the state the first
-      // writes (1 152 B per token) is read — and overwritten in place — by the second while it is still in L2
-      for (long long t0 = 0; t0 < M; t0 += chunk_mlp) {
-        const long long m = M - t0 < chunk_mlp ? M - t0 : chunk_mlp;
-        LayerWs part = flat;
-        part.att_b = ws.att_b + t0 * kE;
-        MMPFN_TRY(out_proj_ln(lw, state + t0 * kE, state_b + t0 * kE, m, MMPFN_BF16, part, st));
-        MMPFN_TRY(mlp(lw, state + t0 * kE, state_b + t0 * kE, m, MMPFN_BF16, part, st));
-      }
-    }
+    if (phase != 1) MMPFN_TRY(mlp(lw, state, state_b, M, MMPFN_BF16, flat, st));
   }
   return MMPFN_OK;
 }

@@ -211,10 +211,10 @@ def test_multi_group_pass_equals_per_group(fit_mode):
     assert torch.isfinite(a).all() and torch.equal(a, b)
 
 
-def test_chunked_schedule_equals_one_estimator_at_a_time():
-    """At 2 000 train rows x 8 estimators the row-wise sublayers run chunk by chunk of the token axis (L2-resident
-    schedule, csrc/api.cu layers_run); one estimator alone stays below the chunking threshold.  Every kernel works
-    row by row, so the logits must be identical bit for bit."""
+def test_eight_estimators_equal_one_at_a_time():
+    """The full-size step (2 000 train rows, 8 estimators in two groups through the multi-segment pass) against
+    every estimator alone through the single-segment entry points: every kernel works row by row and plane by
+    plane, so the logits must be identical bit for bit whatever the batching and launch shapes."""
     from multimodalpfn_b200.classifier import MMPFNClassifier
     from multimodalpfn_b200.engine import B200InferenceEngine
     from multimodalpfn_b200.preprocessing import transform_all

@@ -1,6 +1,7 @@
 """The device-resident step (8 estimators, context rebuilt per call, CUDA graph, L2 flushed between steps) alone:
-    [MMPFN_DEBUG_LIB=1 MMPFN_CHUNK_FEAT=<rounds> MMPFN_CHUNK_MLP=<rounds>] python tools/step_bench.py [dataset]
-Used for A/B timing of schedule variants of the tuning build (the product library reads no environment)."""
+    [MMPFN_DEBUG_LIB=1 <tuning switches>] python tools/step_bench.py [dataset]
+Used for A/B timing of variants of the tuning build (the product library reads no environment), e.g. the
+L2-resident chunked schedule of profiles/r02_chunked_schedule.txt (measured, no gain, removed)."""
 import os
 import sys
 
