@@ -181,13 +181,32 @@ __global__ void __launch_bounds__(R_THREADS, 1) tc_rowgemm_kernel(const __grid_c
         mbar_wait(&a_full[as], (i / kAStages) & 1);
         mbar_wait(&acc_empty[ab], ph ^ 1);
         tc_fence_after();
+        if (EPI == TC_EPI_QKV_ITEMS && jn == 2) {
+          // V is wanted transposed ([d][s] planes): swap the operand roles — W_v rows (d) on the M side, the 128 table
+          // rows (s) on the N side — so that the accumulator already IS V^T (lane = d, column = s) and the epilogue
+          // writes whole 16-byte pieces of a d row instead of 2-byte elements.  192 d rows = two M = 128 MMAs (the
+          // second one's upper 64 lanes multiply whatever follows the W tile in shared memory and are never read).
+          constexpr uint32_t idesc_t = make_idesc(128, R_BM);
 #pragma unroll
-        for (int kb = 0; kb < 3; ++kb) {
-          const uint64_t adesc = make_desc(sbase + R_OFF_A + as * R_A_BYTES + kb * (R_BM * 128), 1024, kSw128);
-          const uint64_t bdesc = make_desc(sbase + R_OFF_W + kb * (R_BN * 128), 1024, kSw128);
+          for (int half = 0; half < 2; ++half)
 #pragma unroll
-          for (int k = 0; k < 4; ++k)
-            umma_bf16(tmem + ab * R_BN, adesc + (uint64_t)(k * 2), bdesc + (uint64_t)(k * 2), idesc, (kb | k) != 0);
+            for (int kb = 0; kb < 3; ++kb) {
+              const uint64_t wdesc = make_desc(sbase + R_OFF_W + kb * (R_BN * 128) + half * (128 * 128), 1024, kSw128);
+              const uint64_t sdesc = make_desc(sbase + R_OFF_A + as * R_A_BYTES + kb * (R_BM * 128), 1024, kSw128);
+#pragma unroll
+              for (int k = 0; k < 4; ++k)
+                umma_bf16(tmem + ab * 256 + half * 128, wdesc + (uint64_t)(k * 2), sdesc + (uint64_t)(k * 2), idesc_t,
+                          (kb | k) != 0);
+            }
+        } else {
+#pragma unroll
+          for (int kb = 0; kb < 3; ++kb) {
+            const uint64_t adesc = make_desc(sbase + R_OFF_A + as * R_A_BYTES + kb * (R_BM * 128), 1024, kSw128);
+            const uint64_t bdesc = make_desc(sbase + R_OFF_W + kb * (R_BN * 128), 1024, kSw128);
+#pragma unroll
+            for (int k = 0; k < 4; ++k)
+              umma_bf16(tmem + ab * R_BN, adesc + (uint64_t)(k * 2), bdesc + (uint64_t)(k * 2), idesc, (kb | k) != 0);
+          }
         }
         umma_commit(&a_empty[as]);
         umma_commit(&acc_full[ab]);
@@ -306,12 +325,12 @@ __global__ void __launch_bounds__(R_THREADS, 1) tc_rowgemm_kernel(const __grid_c
         // and one group of stores per tile; the stores of the previous tile must have read it first
         if (store_leader) bulk_wait_read0();
         epi_bar();
+        if (jn < 2) {
 #pragma unroll 1
-        for (int h = 0; h < kH; ++h) {
-          const uint32_t slot = smem_u32(smem) + R_OFF_Y32 + h * (R_BM * 64);
-          tmem_ld32(trow + h * 32, v);
-          tmem_ld_wait();
-          if (jn < 2) {
+          for (int h = 0; h < kH; ++h) {
+            const uint32_t slot = smem_u32(smem) + R_OFF_Y32 + h * (R_BM * 64);
+            tmem_ld32(trow + h * 32, v);
+            tmem_ld_wait();
             const uint32_t yrow = slot + r * 64;
 #pragma unroll
             for (int k = 0; k < 4; ++k)
@@ -320,14 +339,28 @@ __global__ void __launch_bounds__(R_THREADS, 1) tc_rowgemm_kernel(const __grid_c
                            pack_bf16x2(__uint_as_float(v[8 * k + 2]), __uint_as_float(v[8 * k + 3])),
                            pack_bf16x2(__uint_as_float(v[8 * k + 4]), __uint_as_float(v[8 * k + 5])),
                            pack_bf16x2(__uint_as_float(v[8 * k + 6]), __uint_as_float(v[8 * k + 7])));
-          } else {
-            // element (d, s = r): 64-column block r / 64, row d (128 B), 16-byte piece ((r % 64) / 8) ^ (d & 7)
-            const uint32_t base = slot + (r >> 6) * (kD * 128) + ((r & 7) << 1);
-            const int ch = (r & 63) >> 3;
+          }
+        } else {
+          // the accumulators hold V^T: lanes of half 0 = d rows of heads 0-3 (warp = head), half 1 = heads 4, 5 (warps
+          // 0, 1).  Thread = (head, d = lane): its 128 s values leave as 16 pieces of 16 B — 64-column block c / 2,
+          // row d (128 B), piece ((c & 1) * 4 + k) ^ (d & 7)
+#pragma unroll 1
+          for (int half = 0; half < 2; ++half) {
+            const int h = half * 4 + quarter;
+            if (h >= kH) break;
+            const uint32_t tv = tmem + ab * 256 + half * 128 + ((uint32_t)(quarter * 32) << 16);
+            const uint32_t drow = smem_u32(smem) + R_OFF_Y32 + h * (R_BM * 64) + lane * 128;
+#pragma unroll 1
+            for (int c = 0; c < R_BM / 32; ++c) {
+              tmem_ld32(tv + c * 32, v);
+              tmem_ld_wait();
 #pragma unroll
-            for (int d = 0; d < kD; ++d) {
-              __nv_bfloat16 bv = __float2bfloat16_rn(__uint_as_float(v[d]));
-              st_shared_u16(base + d * 128 + ((ch ^ (d & 7)) << 4), *reinterpret_cast<uint16_t*>(&bv));
+              for (int k = 0; k < 4; ++k)
+                st_shared_v4(drow + (c >> 1) * (kD * 128) + ((((c & 1) * 4 + k) ^ (lane & 7)) << 4),
+                             pack_bf16x2(__uint_as_float(v[8 * k]), __uint_as_float(v[8 * k + 1])),
+                             pack_bf16x2(__uint_as_float(v[8 * k + 2]), __uint_as_float(v[8 * k + 3])),
+                             pack_bf16x2(__uint_as_float(v[8 * k + 4]), __uint_as_float(v[8 * k + 5])),
+                             pack_bf16x2(__uint_as_float(v[8 * k + 6]), __uint_as_float(v[8 * k + 7])));
             }
           }
         }

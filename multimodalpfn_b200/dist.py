@@ -133,7 +133,9 @@ class ShardedEngine:
         """``shard="estimators"`` (default): every estimator's context is built by one owner rank (module docstring).
         ``shard="rows"``: the TRAIN ROWS of every estimator are split over the ranks (``_logits_rows``) — the mode for
         fewer estimators than GPUs, where a single estimator's 50 000-row self-attention would otherwise run on one
-        GPU."""
+        GPU.  ``group="emulate"`` with ``shard="rows"``: the shares of all ``world``
+        ranks run one after the other on this device without any collective (tests of the segment addressing on a
+        single GPU)."""
         self.engine = engine
         self.shard = shard
         self.model = engine.model
@@ -280,8 +282,6 @@ class ShardedEngine:
         n_tr = eng.groups[0]["y_train"].shape[1]
         seg = self.seg_rows
         Sp = (seg + 63) // 64 * 64
-        lo, hi = r * seg, min((r + 1) * seg, n_tr)
-        S_loc = hi - lo
         if self._rows is None:
             bufs = []
             for g, T in zip(eng.groups, self.Ts):
@@ -299,27 +299,40 @@ class ShardedEngine:
         stats = [m.stem_tab_fit(torch.cat([g["X_train"], Xte], dim=1), n_tr)
                  for g, Xte in zip(eng.groups, staged["X_test"])]
         # ---- context build on this rank's rows of every estimator ---------------------------------------------
-        st, stb, views = m._group_buffers([(len(g["idx"]), S_loc, T) for g, T in zip(eng.groups, self.Ts)])
-        segs = []
-        for gi, (g, v) in enumerate(zip(eng.groups, views)):
-            ls, b = g["label_stats"], bufs[gi]
-            m.embed(g["X_train"][:, lo:hi].contiguous(), stats[gi], None if tok_tr is None else tok_tr[lo:hi].contiguous(),
-                    g["y_train"][:, lo:hi].contiguous(), ls[0], ls[1], m.positional_embeddings(self.Ts[gi] - 1),
-                    B=len(g["idx"]), S=S_loc, F=g["F"], x_bstride=S_loc * g["F"], y_bstride=S_loc, nan_flag=flag, out=v)
-            segs.append(dict(B=len(g["idx"]), T=self.Ts[gi], kv=b["ctx"][r, 0], layer_stride=b["block"], seg_rows=seg,
-                             kg=b["kg"], vtg=b["vtg"], gather_stride=b["chunk"], rank=r, n_ranks=W, n_rows_total=n_tr,
-                             bufs=b))
+        # (``group="emulate"``: all W ranks' shares one after the other on this device, no collective — the
+        # single-GPU test of the segment addressing)
+        emulate = self.group == "emulate"
+        shares = []
+        for rk in (range(W) if emulate else [r]):
+            lo, hi = rk * seg, min((rk + 1) * seg, n_tr)
+            S_loc = hi - lo
+            st, stb, views = m._group_buffers([(len(g["idx"]), S_loc, T) for g, T in zip(eng.groups, self.Ts)])
+            segs = []
+            for gi, (g, v) in enumerate(zip(eng.groups, views)):
+                ls, b = g["label_stats"], bufs[gi]
+                m.embed(g["X_train"][:, lo:hi].contiguous(), stats[gi], None if tok_tr is None else tok_tr[lo:hi].contiguous(),
+                        g["y_train"][:, lo:hi].contiguous(), ls[0], ls[1], m.positional_embeddings(self.Ts[gi] - 1),
+                        B=len(g["idx"]), S=S_loc, F=g["F"], x_bstride=S_loc * g["F"], y_bstride=S_loc, nan_flag=flag, out=v)
+                segs.append(dict(B=len(g["idx"]), T=self.Ts[gi], kv=b["ctx"][rk, 0], layer_stride=b["block"], seg_rows=seg,
+                                 kg=b["kg"], vtg=b["vtg"], gather_stride=b["chunk"], rank=rk, n_ranks=W, n_rows_total=n_tr,
+                                 bufs=b))
+            shares.append((st, stb, segs, S_loc, dict(ws_key=f"_share{rk}") if emulate else {}))
         nbytes = 0
+
+        def gather(t):
+            if not emulate:
+                flat = t.view(W, -1)
+                dist.all_gather_into_tensor(flat.view(-1), flat[r] if dev.type == "cuda" else flat[r].clone(), group=self.group)
+            return (W - 1) * (t.numel() // W)
         for l in range(L):
-            m.layers_run(st, stb, segs, S_loc, None, l, l + 1, phase=1)
+            for st, stb, segs, S_loc, kw in shares:
+                m.layers_run(st, stb, segs, S_loc, None, l, l + 1, phase=1, **kw)
             for b in bufs:
-                dist.all_gather_into_tensor(b["kg"].view(-1), b["kg"][r] if dev.type == "cuda" else b["kg"][r].clone(), group=self.group)
-                dist.all_gather_into_tensor(b["vtg"].view(-1), b["vtg"][r] if dev.type == "cuda" else b["vtg"][r].clone(), group=self.group)
-                nbytes += 2 * (W - 1) * b["chunk"]
-            m.layers_run(st, stb, segs, S_loc, None, l, l + 1, phase=2)
+                nbytes += gather(b["kg"]) + gather(b["vtg"])
+            for st, stb, segs, S_loc, kw in shares:
+                m.layers_run(st, stb, segs, S_loc, None, l, l + 1, phase=2, **kw)
         for b in bufs:
-            dist.all_gather_into_tensor(b["ctx"].view(-1), b["ctx"][r].view(-1) if dev.type == "cuda" else b["ctx"][r].reshape(-1).clone(), group=self.group)
-            nbytes += (W - 1) * L * b["block"]
+            nbytes += gather(b["ctx"])
         self.exchange = {"collective": "all_gather_into_tensor", "calls_per_step": 2 * L * len(bufs) + len(bufs),
                          "bytes_received_per_rank": int(nbytes), "mode": "rows", "rows_per_rank": seg}
         # ---- this rank's test rows against every estimator's gathered context ------------------------------------

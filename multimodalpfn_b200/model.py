@@ -251,12 +251,13 @@ class B200PerFeatureTransformer:
                        "mmpfn_layers_test_multi")
 
     def layers_run(self, state, state_b, segs, S: int, n_train: Optional[int], layer_begin: int, layer_end: int,
-                   phase: int = 0):
+                   phase: int = 0, ws_key: str = ""):
         """Layers ``[layer_begin, layer_end)`` over segment states held back to back in ``state`` / ``state_b``
         (``_group_buffers``), with the K/V context of every segment addressed explicitly (``mmpfn_layers_run``).
         ``segs``: dicts ``B, T, kv`` (uint8 tensor view starting at the segment's block of layer 0),
         ``layer_stride`` / ``rank_stride`` (bytes) and ``slots``.  ``n_train=None``: train pass (writes the K/V),
-        else test pass against ``n_train`` context rows."""
+        else test pass against ``n_train`` context rows.  ``phase`` 1 leaves the queries in the workspace for
+        ``phase`` 2: callers that interleave several states between the two name a workspace each (``ws_key``)."""
         n = len(segs)
         def seg(s):
             k = _lib.KvSegment()
@@ -272,7 +273,7 @@ class B200PerFeatureTransformer:
         plain = (_lib.Segment * n)(*[_lib.Segment(int(s["B"]), int(s["T"])) for s in segs])
         S_alloc = max([S] + [int(s.get("seg_rows", 0)) for s in segs]) if n_train is None else S
         nbytes = self.lib.mmpfn_layers_multi_ws_bytes(self._g, plain, n, S_alloc)
-        ws = self._scratch("layers", nbytes)
+        ws = self._scratch("layers" + ws_key, nbytes)
         _lib.check(self.lib.mmpfn_layers_run(self._g, self._w if n_train is None else self._w_test, state.data_ptr(),
                                              state_b.data_ptr(), arr, n, S,
                                              0 if n_train is None else int(n_train), 1 if n_train is None else 0,

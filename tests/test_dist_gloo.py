@@ -118,7 +118,7 @@ class FakeModel:
         state[:, :, T - 1, :] += yy.expand(B, S)[..., None]
         return state, None
 
-    def layers_run(self, state, state_b, segs, S, n_train, l0, l1, phase=0):
+    def layers_run(self, state, state_b, segs, S, n_train, l0, l1, phase=0, ws_key=""):
         off = 0
         for sg in segs:
             B, T = sg["B"], sg["T"]
@@ -280,3 +280,13 @@ def test_rows_mode_rejects_short_tables():
     eng, _, _ = _make_engine(0, 1, 0, n_train=96)
     with pytest.raises(ValueError, match="too few"):
         ShardedEngine(eng, 0, 4, shard="rows")
+
+
+@pytest.mark.parametrize("world", [2, 3])
+def test_rows_mode_emulated_in_process(world):
+    """All ranks' row shares one after the other in this process (no process group): same logits as unsharded."""
+    eng, X_tests, img_test = _make_engine(0, 2, 1, n_train=250)
+    ref = eng.logits(X_tests, img_test, graph=False)
+    sh = ShardedEngine(eng, 0, world, group="emulate", shard="rows")
+    got = sh.logits(X_tests, img_test)
+    assert torch.allclose(got, ref, rtol=0, atol=1e-4), float((got - ref).abs().max())

@@ -237,6 +237,31 @@ def test_eight_estimators_equal_one_at_a_time():
         assert torch.equal(lg[0], all8[i]), i
 
 
+@pytest.mark.parametrize("world,n_est", [(2, 4), (3, 4), (5, 1)])
+def test_row_sharded_context_build_emulated(world, n_est):
+    """dist.ShardedEngine(shard="rows") with the shares of all ranks run one after the other on this GPU: K / V^T planes
+    written into per-rank chunks, queries attending to all chunks through row-segmented tensor maps, the context read
+    as row segments by the test pass (400 train rows: the last segment is ragged, 16 rows at world 5).  Bit-identical
+    to the unsharded engine."""
+    from multimodalpfn_b200.classifier import MMPFNClassifier
+    from multimodalpfn_b200.dist import ShardedEngine
+    from multimodalpfn_b200.preprocessing import transform_all
+    from multimodalpfn_b200.synth import Geometry, make_dataset, make_state_dict
+    geom = Geometry(mgm_heads=2, cap_heads=4)
+    sd = make_state_dict(geom, seed=3)
+    d = make_dataset("pad_ufes_small", 0)
+    clf = MMPFNClassifier(mixer_type="MGM+CAP", mgm_heads=2, cap_heads=4, features_per_group=2, n_estimators=n_est,
+                          model_path=(sd, geom), device="cuda", inference_precision="bf16",
+                          ignore_pretraining_limits=True, random_state=0)
+    clf.fit(d["X_train"], d["img_train"], d["y_train"])
+    eng = clf.executor_
+    X_tests = transform_all(clf.members_, d["X_test"])
+    ref = eng.logits(X_tests, d["img_test"], graph=False).clone()
+    sh = ShardedEngine(eng, 0, world, group="emulate", shard="rows")
+    got = sh.logits(X_tests, d["img_test"])
+    assert torch.isfinite(got).all() and torch.equal(got, ref), float((got - ref).abs().max())
+
+
 def test_graph_replay_survives_scratch_growth():
     """CUDA graphs hold raw pointers into the model's shared scratch buffers; a later, larger call replaces those
     buffers.  Sizes 120 -> 360 -> 120 test rows through the graphed path must each equal the eager path, and the
