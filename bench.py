@@ -314,6 +314,10 @@ def plugin_e2e(args, dev_index, flush, precision):
     return {"value": n_te / float(np.mean(ts)), "unit": "rows/s", "h2d_bytes_per_step": int(h2d),
             "d2h_bytes_per_step": int(p.nbytes), "ms_per_step": float(np.mean(ts)) * 1e3,
             "api": "reference MMPFNClassifier.predict_proba + multimodalpfn_b200.plugin (engine mode)",
+            "host_preprocessing": "the reference's fitted per-member transformers, "
+                                  + ("replayed without sklearn's per-call validation (multimodalpfn_b200/ref_transform.py): "
+                                     if clf.executor_.replay_state == "on" else "the reference's own transform calls: ")
+                                  + clf.executor_.replay_note,
             "T": _token_counts(type("E", (), {"executor_": clf.executor_.ref})())}, p
 
 

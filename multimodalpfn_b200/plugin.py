@@ -72,12 +72,21 @@ class B200PluginEngine:
     (``classifier.py:532-576``) is untouched.
 
     Sub-batches: estimators sharing a preprocessed width, ``stage_size`` at a time, cheapest recipe first (so
-    that the GPU starts early)."""
+    that the GPU starts early).
+
+    ``replay=True`` (default): the fitted preprocessors are also compiled into validation-free replays
+    (``ref_transform.compile_preprocessor``: same arithmetic on the same fitted state, 5-7x cheaper per call).  The
+    first table that arrives is transformed both ways, together with perturbed probe rows; only when every member's
+    replay reproduces the reference's ``transform`` bit for bit are the replays used from then on — and since the
+    host work then is a few milliseconds in all, the estimators run as ONE batched pass instead of the pipeline.
+    A member whose preprocessor is not reproduced (``Unsupported`` step, any mismatch) keeps the whole engine on the
+    reference's own ``transform`` calls."""
 
     def __init__(self, ref_engine, *, device, precision="bf16", pos_emb_device="cuda", model_cls=None,
-                 cache_context=False, stage_size=2):
+                 cache_context=False, stage_size=2, replay=True):
         import numpy as np
         from .engine import B200InferenceEngine
+        from . import ref_transform
         self.ref = ref_engine
         self.preprocessors = ref_engine.preprocessors
         self.ensemble_configs = ref_engine.ensemble_configs
@@ -99,6 +108,15 @@ class B200PluginEngine:
                     eng._img_tok_train = self.stages[0][1].train_image_tokens()
                 self.stages.append((sub, eng))
         self._img_pin = None
+        self._cache_context = cache_context
+        # "unverified" -> "on" | "off" at the first table (see the class docstring); self.replay_note says why
+        self.replay_state, self.replay_note, self._fast, self._all = "off", "disabled", None, None
+        if replay:
+            try:
+                self._fast = [ref_transform.compile_preprocessor(p) for p in self.preprocessors]
+                self.replay_state, self.replay_note = "unverified", "compiled, not yet compared with the reference"
+            except ref_transform.Unsupported as exc:
+                self.replay_note = f"not reproduced: {exc}"
 
     def _upload_image(self, image_test):
         import numpy as np
@@ -114,10 +132,34 @@ class B200PluginEngine:
         self._img_pin.numpy()[...] = img
         return self._img_pin.to(self.model.device, non_blocking=True)
 
+    def _verify_replay(self, X):
+        from . import ref_transform
+        from .engine import B200InferenceEngine
+        probe = ref_transform.make_probe(X)
+        for i, (pre, fast) in enumerate(zip(self.preprocessors, self._fast)):
+            if self.members[i]["X_train"] is None:
+                continue
+            if not (ref_transform.verify(pre, fast, X) and ref_transform.verify(pre, fast, probe)):
+                self.replay_state, self.replay_note = "off", f"replay of member {i} differs from the reference's transform"
+                return
+        self._all = B200InferenceEngine(self.model, self.members, self.ref.image_train, cache_context=self._cache_context)
+        self._all._img_tok_train = self.stages[0][1].train_image_tokens()
+        self.replay_state, self.replay_note = "on", "bit-identical to the reference's transform on the first table and its probes"
+
     def iter_outputs(self, X, image_test, *, device=None, autocast=None):
         import numpy as np
         image_dev = self._upload_image(image_test)
         outs = [None] * len(self.members)
+        if X is not None and self.replay_state == "unverified":
+            self._verify_replay(X)
+        if X is not None and self.replay_state == "on":
+            X_tests = [None if m["X_train"] is None else np.asarray(f(X), dtype=np.float32)
+                       for m, f in zip(self.members, self._fast)]
+            lg = self._all.logits(X_tests, None, image_dev=image_dev)
+            self._all.check_nan()
+            for out, cfg in zip(lg, self.ensemble_configs):
+                yield out, cfg
+            return
         for sub, eng in self.stages:
             X_tests = [None if X is None or self.members[i]["X_train"] is None
                        else np.asarray(self.preprocessors[i].transform(X).X, dtype=np.float32) for i in sub]   # inference.py:303
@@ -130,7 +172,8 @@ class B200PluginEngine:
             yield lg, cfg
 
 
-def install(precision: str = "bf16", model_cls=None, pos_emb_device: str = "cuda", mode: str = "engine"):
+def install(precision: str = "bf16", model_cls=None, pos_emb_device: str = "cuda", mode: str = "engine",
+            replay: bool = True):
     """Patch ``create_inference_engine`` where the reference's estimators look it up
     (``mmpfn.models.mmpfn.classifier`` and ``.regressor``: ``MMPFNRegressor`` runs the same forward with a
     bar-distribution head, regressor.py:577-730); returns an ``uninstall()``.
@@ -138,7 +181,8 @@ def install(precision: str = "bf16", model_cls=None, pos_emb_device: str = "cuda
     ``mode="model"``: the reference's engine keeps its serial per-estimator loop and only its ``.model`` is
     swapped (one B = 1 CUDA forward per estimator).  ``mode="engine"`` (default): the engine object itself is
     replaced by ``B200PluginEngine`` (all estimators in one batched pass) — what SURVEY.md section 7 step 1(i)
-    describes.  Both leave every line of the reference's ``fit`` / ``predict_proba`` in charge."""
+    describes.  Both leave every line of the reference's ``fit`` / ``predict_proba`` in charge; ``replay=False`` also
+    keeps the reference's own per-member ``transform`` calls at predict time (``B200PluginEngine`` docstring)."""
     import mmpfn.models.mmpfn.classifier as C
     import mmpfn.models.mmpfn.regressor as R
 
@@ -155,7 +199,7 @@ def install(precision: str = "bf16", model_cls=None, pos_emb_device: str = "cuda
             if getattr(dev, "type", str(dev)) == "cuda" and hasattr(engine, "model"):
                 if mode == "engine" and hasattr(engine, "preprocessors") and hasattr(engine, "X_trains"):
                     return B200PluginEngine(engine, device=dev, precision=precision, pos_emb_device=pos_emb_device,
-                                            model_cls=model_cls)
+                                            model_cls=model_cls, replay=replay)
                 engine.model = convert(engine.model, device=dev, precision=precision, model_cls=model_cls,
                                        pos_emb_device=pos_emb_device)
             return engine

@@ -65,6 +65,8 @@ def test_plugin_real_model_vs_reference(tmp_path, dataset, n_est, heads):
                 uninstall()
             assert isinstance(clf.executor_.model, B200PerFeatureTransformer)      # the swap happened
             assert isinstance(clf.executor_, plugin.B200PluginEngine) == (mode == "engine")
+            if mode == "engine":      # the fitted preprocessors were replayed, after the bit-for-bit check at the first table
+                assert clf.executor_.replay_state == "on", clf.executor_.replay_note
             assert _lib.launch_count() > l0                                          # ... and our kernels ran
             assert got.shape == ref.shape and got.dtype == ref.dtype
             assert np.allclose(got.sum(1), 1.0, atol=1e-5)
@@ -73,6 +75,38 @@ def test_plugin_real_model_vs_reference(tmp_path, dataset, n_est, heads):
             check_proba(got, ref, tol + slack, f"plug-in[{mode}] {dataset} {precision} vs {what}")
     assert C.create_inference_engine.__name__ == "create_inference_engine"
     assert not getattr(C.create_inference_engine, "_mmpfn_b200", False)              # uninstalled
+
+
+def test_plugin_replay_equals_reference_transforms(tmp_path):
+    """Engine mode with the fitted preprocessors replayed (one batched pass) against engine mode on the reference's own
+    ``transform`` calls (pipelined sub-batches): the tables that reach the model are bit-identical and the kernels are
+    batching-invariant, so the probabilities must be EQUAL — also on a second table (no verification any more) with
+    NaNs and category codes the fit never saw."""
+    from multimodalpfn_b200 import plugin
+    from multimodalpfn_b200.synth import Geometry, make_dataset
+    ref_compat.install()
+    import mmpfn.models.mmpfn.classifier as C
+
+    geom = Geometry(mgm_heads=2, cap_heads=4)
+    path = _checkpoint(tmp_path, geom, seed=11)
+    d = make_dataset("pad_ufes_small", 0)
+    X2 = d["X_test"].copy()
+    rng = np.random.default_rng(3)
+    X2[rng.random(X2.shape) < 0.05] = np.nan
+    X2[::7, 15] = 9.0                                  # an unseen level of a categorical column
+    X2[::5, 20] *= 4.0                                 # beyond the fitted quantile range
+    kw = dict(mixer_type="MGM+CAP", mgm_heads=2, cap_heads=4, features_per_group=2, n_estimators=8, model_path=path,
+              ignore_pretraining_limits=True, random_state=0, device="cuda")
+    out = {}
+    for replay in (True, False):
+        uninstall = plugin.install(precision="bf16", mode="engine", replay=replay)
+        try:
+            clf = C.MMPFNClassifier(**kw).fit(d["X_train"], d["img_train"], d["y_train"])
+            out[replay] = (clf.predict_proba(d["X_test"], d["img_test"]), clf.predict_proba(X2, d["img_test"]))
+        finally:
+            uninstall()
+        assert clf.executor_.replay_state == ("on" if replay else "off"), clf.executor_.replay_note
+    assert np.array_equal(out[True][0], out[False][0]) and np.array_equal(out[True][1], out[False][1])
 
 
 @pytest.mark.parametrize("mode", ["engine", "model"])
@@ -110,6 +144,8 @@ def test_plugin_regressor_vs_reference(tmp_path, mode):
         finally:
             uninstall()
         assert isinstance(reg.executor_, plugin.B200PluginEngine) == (mode == "engine")
+        if mode == "engine":
+            print(f"[plug-in regressor] preprocessor replay: {reg.executor_.replay_state} ({reg.executor_.replay_note})")
         dl = float((got["logits"] - ref["logits"]).abs().max())
         dm = float(np.abs(got["mean"] - ref["mean"]).max())
         dq = max(float(np.abs(a - b).max()) for a, b in zip(got["quantiles"], ref["quantiles"]))
