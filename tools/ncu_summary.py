@@ -47,5 +47,5 @@ for r in rows[2:]:
                    "tensor_pipe_pct": float(vals["sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active"]),
                    "issue_active_pct": float(vals["smsp__issue_active.avg.pct_of_peak_sustained_active"]),
                    "instructions": float(vals["smsp__inst_executed.sum"]),
-                   "source": "profiles/r02_ncu_kernels_v2_summary.txt (ncu --set full --clock-control none, one launch, tools/prof_kernels.py)"},
+                   "source": "profiles/<the summary written next to this json> (ncu --set full --clock-control none, one launch, tools/prof_kernels.py)"},
                   open(sys.argv[2], "w"), indent=1)
