@@ -257,6 +257,13 @@ def test_sharded_engine_world4_one_each():
     assert [r[3] for r in res] == [[2], [3], [0], [1]]          # groups in feature-count order: F=4 (members 2, 3) first
 
 
+def test_sharded_engine_world4_split():
+    res = _run(4)                                                         # 4 + 4 estimators on 4 ranks: one of each group per rank
+    assert all(r[1] and r[2] for r in res), res
+    assert all(r[4] == "split" for r in res)
+    assert [r[3] for r in res] == [[0, 4], [1, 5], [2, 6], [3, 7]]
+
+
 def test_sharded_engine_world2_broadcast_fallback():
     res = _run(2, n_a=3, n_b=2)                                           # 3 + 2 estimators on 2 ranks: round-robin + broadcast
     assert all(r[1] and r[2] for r in res), res
