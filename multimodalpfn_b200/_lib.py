@@ -85,6 +85,7 @@ SIGNATURES = {
     "mmpfn_linear_ln_bf16": (c_int, [c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_void_p]),
     "mmpfn_mlp_bf16": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_void_p]),
     "mmpfn_feature_attention_bf16": (c_int, [c_void_p, c_void_p, c_ll, c_int, c_void_p]),
+    "mmpfn_feature_qkv_attention_bf16": (c_int, [c_void_p, c_void_p, c_ll, c_int, c_void_p, c_void_p]),
     "mmpfn_item_attention_bf16": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int,
                                           c_int, c_void_p, c_void_p]),
 }

@@ -573,17 +573,35 @@ static int layers_run(const mmpfn_geometry* g, const mmpfn_weights* w, float* st
   const int Sp = kv_pad(Sa), Np = kv_pad(n_train);
   LayerWs flat{};
   flat.hid_b = ws.hid_b; flat.qkv_b = ws.hid_b; flat.att_b = ws.att_b;
+#ifdef MMPFN_DEBUG
+  // tuning build only: MMPFN_FEAT_FUSED=0 takes the two-kernel form of the feature sublayer's first half
+  static int feat_fused = -1;
+  if (feat_fused < 0) {
+    const char* e = getenv("MMPFN_FEAT_FUSED");
+    feat_fused = e ? atoi(e) : 1;
+  }
+#else
+  constexpr bool feat_fused = true;
+#endif
   for (int l = layer_begin; l < layer_end; ++l) {
     const LayerW lw = layer_w(w, l);
     // features: QKV over all tokens, attention per segment (rows of T_i tokens), out-projection + LN over all
     if (phase != 2) {
-      TcGemm a{};
-      a.A = state_b; a.W = lw.fqkv_b; a.M = (int)M; a.N = 3 * kE; a.K = kE; a.epi = TC_EPI_BF16; a.out_bf16 = ws.hid_b;
-      MMPFN_TRY(proj_gemm(a, st));
+      // rows of up to 32 tokens: projection and attention in one kernel per segment (the qkv block stays on chip);
+      // wider rows: one flat projection, then the attention per segment
+      bool fused = feat_fused;
+      for (int i = 0; i < n_seg; ++i) fused = fused && feat_qkv_attn_supported(segs[i].T);
+      if (!fused) {
+        TcGemm a{};
+        a.A = state_b; a.W = lw.fqkv_b; a.M = (int)M; a.N = 3 * kE; a.K = kE; a.epi = TC_EPI_BF16; a.out_bf16 = ws.hid_b;
+        MMPFN_TRY(proj_gemm(a, st));
+      }
       long long off = 0;
       for (int i = 0; i < n_seg; ++i) {
-        MMPFN_TRY(launch_feat_attn_bf16(ws.hid_b + off * 3 * kE, ws.att_b + off * kE, (long long)segs[i].B * S, segs[i].T, st));
-        off += (long long)segs[i].B * S * segs[i].T;
+        const long long m = (long long)segs[i].B * S * segs[i].T;
+        if (fused) MMPFN_TRY(launch_feat_qkv_attn(state_b + off * kE, lw.fqkv_b, m, segs[i].T, ws.att_b + off * kE, st));
+        else MMPFN_TRY(launch_feat_attn_bf16(ws.hid_b + off * 3 * kE, ws.att_b + off * kE, (long long)segs[i].B * S, segs[i].T, st));
+        off += m;
       }
       TcGemm o{};
       o.A = ws.att_b; o.W = lw.fout_b; o.M = (int)M; o.N = kE; o.K = kE; o.epi = TC_EPI_RESID_LN;
@@ -785,6 +803,13 @@ int mmpfn_feature_attention_bf16(const uint16_t* qkv, uint16_t* att, long long n
   MMPFN_TRY(require_device());
   if (!qkv || !att || n_rows < 1 || T < 1) { set_error("feature_attention_bf16: bad arguments"); return MMPFN_EINVAL; }
   return launch_feat_attn_bf16(qkv, att, n_rows, T, (cudaStream_t)stream);
+}
+
+int mmpfn_feature_qkv_attention_bf16(const uint16_t* x, const uint16_t* w_qkv, long long n_rows, int T, uint16_t* att,
+                                     void* stream) {
+  MMPFN_TRY(require_device());
+  if (!x || !w_qkv || !att || n_rows < 1 || T < 2) { set_error("feature_qkv_attention: bad arguments"); return MMPFN_EINVAL; }
+  return launch_feat_qkv_attn(x, w_qkv, n_rows * T, T, att, (cudaStream_t)stream);
 }
 
 }  // extern "C"

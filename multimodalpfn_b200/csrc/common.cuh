@@ -124,6 +124,9 @@ int launch_kv_extract_f32(const float* qkv, float* kv, int B, int S, int T, cuda
 // attention between features: qkv [rows = n_seq*T][3*kE] (q|k|v, head-major) -> att [rows][kE]
 int launch_feat_attn_f32(const float* qkv, float* att, long long n_seq, int T, cudaStream_t st);
 int launch_feat_attn_bf16(const uint16_t* qkv, uint16_t* att, long long n_seq, int T, cudaStream_t st);
+// QKV projection + feature attention in one kernel (kernels_featfused.cu); T <= 32
+bool feat_qkv_attn_supported(int T);
+int launch_feat_qkv_attn(const uint16_t* x, const uint16_t* w_qkv, long long M, int T, uint16_t* att, cudaStream_t st);
 
 // attention between items, fp32 flash kernel.  For plane p in [0, planes) and head h:
 //   q row i  at  q  + plane_off(q)  + i*q_row  + h*kD          (n_q rows)

@@ -7,6 +7,7 @@
 //   feat_attn_kernel    per-row attention across tokens    layer.py:332-339
 //   item_attn_f32       flash attention across items       layer.py:341-379
 #include "common.cuh"
+#include "feat_attn_core.cuh"
 
 namespace mmpfn {
 
@@ -282,20 +283,6 @@ int launch_feat_attn(const TIn* qkv, TOut* att, long long n_seq, int T, cudaStre
 namespace {
 constexpr int FA_ROW_BYTES = 3 * kE * 2 + 16;   // 1168
 
-__device__ __forceinline__ void ldsm_x4(uint32_t (&r)[4], uint32_t addr) {
-  asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0,%1,%2,%3}, [%4];"
-               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(addr));
-}
-__device__ __forceinline__ void ldsm_x4_t(uint32_t (&r)[4], uint32_t addr) {
-  asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0,%1,%2,%3}, [%4];"
-               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(addr));
-}
-__device__ __forceinline__ void mma_bf16(float (&d)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
-  asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
-               : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
-               : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
-}
-
 // KT = number of 16-key tiles the register file is sized for (T <= 16*KT).
 // A CTA walks table rows blockIdx.x, blockIdx.x + gridDim.x, ... with two staging buffers: the qkv block
 // of the next row streams in (cp.async) while the current row is computed, so the DRAM latency of a row is
@@ -344,97 +331,12 @@ __global__ void __launch_bounds__(384) feat_attn_mma_kernel(const uint16_t* __re
   __syncthreads();
   const uint32_t sbase = sbase0 + cur * buf_bytes;
 
-  const float c2 = 0.17677669529663687f * 1.4426950408889634f;   // log2(e)/sqrt(d)
   const int n_items = kH * n_kt;
   for (int item = warp; item < n_items; item += (blockDim.x >> 5)) {
     const int h = item / n_kt, mt = item % n_kt;
-    // Q fragments: 16 queries x 32 d = 2 k-steps
-    uint32_t qa[2][4];
-#pragma unroll
-    for (int ks = 0; ks < 2; ++ks)
-      ldsm_x4(qa[ks], sbase + (mt * 16 + (lane & 15)) * FA_ROW_BYTES + (h * kD + ks * 16 + (lane >> 4) * 8) * 2);
-    // S = Q K^T
-    float sacc[2 * KT][4];
-#pragma unroll
-    for (int nt = 0; nt < 2 * KT; ++nt) { sacc[nt][0] = sacc[nt][1] = sacc[nt][2] = sacc[nt][3] = 0.f; }
-#pragma unroll
-    for (int kt = 0; kt < KT; ++kt) {
-      if (kt < n_kt) {
-#pragma unroll
-        for (int ks = 0; ks < 2; ++ks) {
-          uint32_t kb[4];
-          const int mi = lane >> 3;
-          ldsm_x4(kb, sbase + (kt * 16 + (mi >> 1) * 8 + (lane & 7)) * FA_ROW_BYTES +
-                          (kE + h * kD + ks * 16 + (mi & 1) * 8) * 2);
-          mma_bf16(sacc[2 * kt], qa[ks], kb[0], kb[1]);
-          mma_bf16(sacc[2 * kt + 1], qa[ks], kb[2], kb[3]);
-        }
-      }
-    }
-    // softmax over the T real keys; thread holds rows (lane/4) and (lane/4 + 8), key columns (lane%4)*2 + {0,1}
-    float mx0 = -INFINITY, mx1 = -INFINITY;
-#pragma unroll
-    for (int nt = 0; nt < 2 * KT; ++nt) {
-      if (nt < 2 * n_kt) {
-        const int key = nt * 8 + (lane & 3) * 2;
-        if (key >= T) { sacc[nt][0] = -INFINITY; sacc[nt][2] = -INFINITY; }
-        if (key + 1 >= T) { sacc[nt][1] = -INFINITY; sacc[nt][3] = -INFINITY; }
-        mx0 = fmaxf(mx0, fmaxf(sacc[nt][0], sacc[nt][1]));
-        mx1 = fmaxf(mx1, fmaxf(sacc[nt][2], sacc[nt][3]));
-      }
-    }
-    mx0 = fmaxf(mx0, __shfl_xor_sync(0xffffffffu, mx0, 1));
-    mx0 = fmaxf(mx0, __shfl_xor_sync(0xffffffffu, mx0, 2));
-    mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, 1));
-    mx1 = fmaxf(mx1, __shfl_xor_sync(0xffffffffu, mx1, 2));
-    const float mc0 = mx0 * c2, mc1 = mx1 * c2;
-    float l0 = 0.f, l1 = 0.f;
-    float oacc[4][4];
-#pragma unroll
-    for (int nt = 0; nt < 4; ++nt) { oacc[nt][0] = oacc[nt][1] = oacc[nt][2] = oacc[nt][3] = 0.f; }
-#pragma unroll
-    for (int kt = 0; kt < KT; ++kt) {
-      if (kt < n_kt) {
-        uint32_t pa[4];
-        {
-          const float p00 = fast_exp2f(fmaf(sacc[2 * kt][0], c2, -mc0)), p01 = fast_exp2f(fmaf(sacc[2 * kt][1], c2, -mc0));
-          const float p10 = fast_exp2f(fmaf(sacc[2 * kt][2], c2, -mc1)), p11 = fast_exp2f(fmaf(sacc[2 * kt][3], c2, -mc1));
-          const float q00 = fast_exp2f(fmaf(sacc[2 * kt + 1][0], c2, -mc0)), q01 = fast_exp2f(fmaf(sacc[2 * kt + 1][1], c2, -mc0));
-          const float q10 = fast_exp2f(fmaf(sacc[2 * kt + 1][2], c2, -mc1)), q11 = fast_exp2f(fmaf(sacc[2 * kt + 1][3], c2, -mc1));
-          l0 += (p00 + p01) + (q00 + q01);
-          l1 += (p10 + p11) + (q10 + q11);
-          pa[0] = pack_bf16x2(p00, p01); pa[1] = pack_bf16x2(p10, p11);
-          pa[2] = pack_bf16x2(q00, q01); pa[3] = pack_bf16x2(q10, q11);
-        }
-        // V fragments (transposed load): 16 keys x 32 d = 4 n-tiles
-#pragma unroll
-        for (int np = 0; np < 2; ++np) {
-          uint32_t vb[4];
-          const int mi = lane >> 3;
-          ldsm_x4_t(vb, sbase + (kt * 16 + (mi & 1) * 8 + (lane & 7)) * FA_ROW_BYTES +
-                            (2 * kE + h * kD + np * 16 + (mi >> 1) * 8) * 2);
-          mma_bf16(oacc[2 * np], pa, vb[0], vb[1]);
-          mma_bf16(oacc[2 * np + 1], pa, vb[2], vb[3]);
-        }
-      }
-    }
-    l0 += __shfl_xor_sync(0xffffffffu, l0, 1);
-    l0 += __shfl_xor_sync(0xffffffffu, l0, 2);
-    l1 += __shfl_xor_sync(0xffffffffu, l1, 1);
-    l1 += __shfl_xor_sync(0xffffffffu, l1, 2);
-    const float i0 = 1.0f / l0, i1 = 1.0f / l1;
-    // The output block of this item overwrites the item's own Q block in shared memory (16 tokens x 64 B
-    // that only this warp read, and it holds them in registers since the first ldmatrix): the row then
-    // leaves as whole 16-byte pieces, coalesced, instead of 4-byte stores scattered over 8 token rows.
-    const int q0 = mt * 16 + (lane >> 2), q1 = q0 + 8;
-    const uint32_t so0 = sbase + q0 * FA_ROW_BYTES + (h * kD + (lane & 3) * 2) * 2;
-    const uint32_t so1 = sbase + q1 * FA_ROW_BYTES + (h * kD + (lane & 3) * 2) * 2;
-    __syncwarp();
-#pragma unroll
-    for (int nt = 0; nt < 4; ++nt) {
-      asm volatile("st.shared.b32 [%0], %1;" ::"r"(so0 + nt * 16), "r"(pack_bf16x2(oacc[nt][0] * i0, oacc[nt][1] * i0)) : "memory");
-      asm volatile("st.shared.b32 [%0], %1;" ::"r"(so1 + nt * 16), "r"(pack_bf16x2(oacc[nt][2] * i1, oacc[nt][3] * i1)) : "memory");
-    }
+    // (the output block of the item overwrites the item's own Q block in shared memory: the row then leaves as whole
+    // 16-byte pieces, coalesced, instead of 4-byte stores scattered over 8 token rows)
+    feat_attn_item<KT>(sbase, FA_ROW_BYTES, h * kD * 2, (kE + h * kD) * 2, (2 * kE + h * kD) * 2, T, n_kt, mt, lane);
   }
   __syncthreads();
   {

@@ -204,6 +204,36 @@ def test_feature_attention_bf16(n_rows, T):
     assert (att.float() - ref).abs().max().item() < 0.03      # P and the output rounded to bf16, O(1) values
 
 
+@pytest.mark.parametrize("n_rows,T", [(1, 2), (5, 3), (7, 16), (301, 20), (2000, 27), (333, 32), (9200, 27)])
+def test_feature_qkv_attention_fused(n_rows, T):
+    """QKV projection + feature attention in one kernel (csrc/kernels_featfused.cu) against the two-kernel form
+    (persistent tcgen05 projection, then the mma.sync attention) on the same operands: the same MMAs in the same
+    order and the same attention core, so the outputs must be EQUAL; pad rows of the destination stay untouched."""
+    lib = _lib.load()
+    g = torch.Generator().manual_seed(n_rows * 7 + T)
+    M = n_rows * T
+    x = torch.randn(M, 192, generator=g).cuda().to(torch.bfloat16)
+    w = (torch.randn(576, 192, generator=g) * 0.1).cuda().to(torch.bfloat16)
+    qkv = torch.empty(M, 576, dtype=torch.bfloat16, device="cuda")
+    ref = torch.empty(M, 192, dtype=torch.bfloat16, device="cuda")
+    _lib.check(lib.mmpfn_linear_bf16(x.data_ptr(), w.data_ptr(), M, 576, 192, 0, qkv.data_ptr(), _stream()), "linear")
+    _lib.check(lib.mmpfn_feature_attention_bf16(qkv.data_ptr(), ref.data_ptr(), n_rows, T, _stream()), "feat_attn")
+    got = torch.full((M + 3, 192), float("nan"), dtype=torch.bfloat16, device="cuda")
+    _lib.check(lib.mmpfn_feature_qkv_attention_bf16(x.data_ptr(), w.data_ptr(), n_rows, T, got.data_ptr(), _stream()), "fused")
+    torch.cuda.synchronize()
+    assert torch.isnan(got[M:].float()).all()
+    assert not torch.isnan(got[:M].float()).any()
+    assert torch.equal(got[:M], ref), float((got[:M].float() - ref.float()).abs().max())
+
+
+def test_feature_qkv_attention_fused_rejects_wide_rows():
+    lib = _lib.load()
+    x = torch.zeros(66, 192, dtype=torch.bfloat16, device="cuda")
+    w = torch.zeros(576, 192, dtype=torch.bfloat16, device="cuda")
+    out = torch.zeros(66, 192, dtype=torch.bfloat16, device="cuda")
+    assert lib.mmpfn_feature_qkv_attention_bf16(x.data_ptr(), w.data_ptr(), 2, 33, out.data_ptr(), _stream()) == -4      # MMPFN_EUNSUPPORTED
+
+
 @pytest.mark.parametrize("mgm,cap,rows,n_tok", [(2, 4, 77, 1), (8, 8, 300, 2), (64, 24, 130, 1)])
 def test_image_stem_bf16_vs_fp32(mgm, cap, rows, n_tok):
     """MGM + CAP stem (transformer.py:33-88): the bf16 mode (gated projection on tcgen05, bf16 operands) against the
