@@ -76,21 +76,22 @@ __device__ __forceinline__ void feat_attn_item(uint32_t sbase, int row_bytes, in
   float oacc[4][4];
 #pragma unroll
   for (int nt = 0; nt < 4; ++nt) { oacc[nt][0] = oacc[nt][1] = oacc[nt][2] = oacc[nt][3] = 0.f; }
+  // P of one 16-key tile as the A fragment of P V (bf16), row sums on the side
+  auto probs = [&](int kt, uint32_t (&pa)[4]) {
+    const float p00 = fast_exp2f(fmaf(sacc[2 * kt][0], c2, -mc0)), p01 = fast_exp2f(fmaf(sacc[2 * kt][1], c2, -mc0));
+    const float p10 = fast_exp2f(fmaf(sacc[2 * kt][2], c2, -mc1)), p11 = fast_exp2f(fmaf(sacc[2 * kt][3], c2, -mc1));
+    const float q00 = fast_exp2f(fmaf(sacc[2 * kt + 1][0], c2, -mc0)), q01 = fast_exp2f(fmaf(sacc[2 * kt + 1][1], c2, -mc0));
+    const float q10 = fast_exp2f(fmaf(sacc[2 * kt + 1][2], c2, -mc1)), q11 = fast_exp2f(fmaf(sacc[2 * kt + 1][3], c2, -mc1));
+    l0 += (p00 + p01) + (q00 + q01);
+    l1 += (p10 + p11) + (q10 + q11);
+    pa[0] = pack_bf16x2(p00, p01); pa[1] = pack_bf16x2(p10, p11);
+    pa[2] = pack_bf16x2(q00, q01); pa[3] = pack_bf16x2(q10, q11);
+  };
 #pragma unroll
   for (int kt = 0; kt < KT; ++kt) {
     if (kt < n_kt) {
       uint32_t pa[4];
-      {
-        const float p00 = fast_exp2f(fmaf(sacc[2 * kt][0], c2, -mc0)), p01 = fast_exp2f(fmaf(sacc[2 * kt][1], c2, -mc0));
-        const float p10 = fast_exp2f(fmaf(sacc[2 * kt][2], c2, -mc1)), p11 = fast_exp2f(fmaf(sacc[2 * kt][3], c2, -mc1));
-        const float q00 = fast_exp2f(fmaf(sacc[2 * kt + 1][0], c2, -mc0)), q01 = fast_exp2f(fmaf(sacc[2 * kt + 1][1], c2, -mc0));
-        const float q10 = fast_exp2f(fmaf(sacc[2 * kt + 1][2], c2, -mc1)), q11 = fast_exp2f(fmaf(sacc[2 * kt + 1][3], c2, -mc1));
-        l0 += (p00 + p01) + (q00 + q01);
-        l1 += (p10 + p11) + (q10 + q11);
-        pa[0] = pack_bf16x2(p00, p01); pa[1] = pack_bf16x2(p10, p11);
-        pa[2] = pack_bf16x2(q00, q01); pa[3] = pack_bf16x2(q10, q11);
-      }
-      // V fragments (transposed load): 16 keys x 32 d = 4 n-tiles
+      probs(kt, pa);
 #pragma unroll
       for (int np = 0; np < 2; ++np) {
         uint32_t vb[4];
