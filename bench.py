@@ -655,17 +655,25 @@ def kernel_breakdown(torch, _lib, dev, S, T, B, peaks):
         d.update(kw)
         return d
 
-    # fused QKV projection (persistent tcgen05 kernel, resident W tile)
+    # feature sublayer, first half: QKV projection + attention between the T tokens of a table row in ONE kernel
+    # (tcgen05 projection, mma.sync attention on the q/k/v block in shared memory): reads x, writes [M][192].
+    # Bound by the legacy mma.sync rate of the attention items (profiles/r02_feature_fused_knockouts.txt), not by HBM;
+    # the two kernels it replaces (timed below for reference) move 4x the bytes.
     W = (torch.randn(3 * E, E, device=dev, generator=g) / E ** 0.5).to(torch.bfloat16)
+    att = torch.empty(M, E, device=dev, dtype=torch.bfloat16)
+    ms = _time_kernel(torch, lambda: _lib.check(
+        lib.mmpfn_feature_qkv_attention_bf16(A.data_ptr(), W.data_ptr(), B * S, T, att.data_ptr(), st), "feat_fused"))
+    res["feature_qkv_attention_fused"] = entry(ms, 2.0 * M * 3 * E * E + 4.0 * M * T * E, 2.0 * (M * E + 3 * E * E + M * E),
+                                               M=M, T=T, on_path=True)
     O = torch.empty(M, 3 * E, device=dev, dtype=torch.bfloat16)
     ms = _time_kernel(torch, lambda: _lib.check(
         lib.mmpfn_linear_bf16(A.data_ptr(), W.data_ptr(), M, 3 * E, E, 0, O.data_ptr(), st), "qkv"))
-    res["qkv_proj"] = entry(ms, 2.0 * M * 3 * E * E, 2.0 * (M * E + 3 * E * E + M * 3 * E), M=M, N=3 * E, K=E)
-    # feature-axis attention (per table row: 6 heads over T tokens): reads the qkv block, writes [M][192]
-    att = torch.empty(M, E, device=dev, dtype=torch.bfloat16)
+    res["qkv_proj"] = entry(ms, 2.0 * M * 3 * E * E, 2.0 * (M * E + 3 * E * E + M * 3 * E), M=M, N=3 * E, K=E,
+                            on_path="rows wider than 32 tokens only")
     ms = _time_kernel(torch, lambda: _lib.check(
         lib.mmpfn_feature_attention_bf16(O.data_ptr(), att.data_ptr(), B * S, T, st), "feat_attn"))
-    res["feature_attention"] = entry(ms, 4.0 * M * T * E, 2.0 * (M * 3 * E + M * E), M=M, T=T)
+    res["feature_attention"] = entry(ms, 4.0 * M * T * E, 2.0 * (M * 3 * E + M * E), M=M, T=T,
+                                     on_path="rows wider than 32 tokens only")
     del O, att
     # item-attention QKV projection + scatter into q/k/v^T planes (+ head-0 context): [B][S][T] tiles by 4-D TMA
     Sp = (S + 63) // 64 * 64
