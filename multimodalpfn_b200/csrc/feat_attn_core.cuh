@@ -51,7 +51,7 @@ __device__ __forceinline__ void feat_attn_item(uint32_t sbase, int row_bytes, in
         const int mi = lane >> 3;
         fa_ldsm_x4(kb, sbase + (kt * 16 + (mi >> 1) * 8 + (lane & 7)) * row_bytes + k_off + (ks * 16 + (mi & 1) * 8) * 2);
         fa_mma_bf16(sacc[2 * kt], qa[ks], kb[0], kb[1]);
-        fa_mma_bf16(sacc[2 * kt + 1], qa[ks], kb[2], kb[3]);
+        if (kt * 16 + 8 < T) fa_mma_bf16(sacc[2 * kt + 1], qa[ks], kb[2], kb[3]);   // (an 8-key tile past T is masked anyway)
       }
     }
   }
