@@ -669,11 +669,11 @@ def kernel_breakdown(torch, _lib, dev, S, T, B, peaks):
     ms = _time_kernel(torch, lambda: _lib.check(
         lib.mmpfn_linear_bf16(A.data_ptr(), W.data_ptr(), M, 3 * E, E, 0, O.data_ptr(), st), "qkv"))
     res["qkv_proj"] = entry(ms, 2.0 * M * 3 * E * E, 2.0 * (M * E + 3 * E * E + M * 3 * E), M=M, N=3 * E, K=E,
-                            on_path="rows wider than 32 tokens only")
+                            on_path="rows wider than 64 tokens only")
     ms = _time_kernel(torch, lambda: _lib.check(
         lib.mmpfn_feature_attention_bf16(O.data_ptr(), att.data_ptr(), B * S, T, st), "feat_attn"))
     res["feature_attention"] = entry(ms, 4.0 * M * T * E, 2.0 * (M * 3 * E + M * E), M=M, T=T,
-                                     on_path="rows wider than 32 tokens only")
+                                     on_path="rows wider than 64 tokens only")
     del O, att
     # item-attention QKV projection + scatter into q/k/v^T planes (+ head-0 context): [B][S][T] tiles by 4-D TMA
     Sp = (S + 63) // 64 * 64

@@ -281,7 +281,7 @@ int mmpfn_item_attention_bf16(const uint16_t* q, const uint16_t* k, const uint16
 int mmpfn_feature_attention_bf16(const uint16_t* qkv, uint16_t* att, long long n_rows, int T, void* stream);
 
 /* QKV projection + feature-axis attention in ONE kernel (multi_head_attention.py:430-434 + layer.py:332-339 for the
- * feature axis): the [tokens][576] qkv block never leaves the SM.  What the bf16 layer passes run for T <= 32
+ * feature axis): the [tokens][576] qkv block never leaves the SM.  What the bf16 layer passes run for T <= 64
  * (MMPFN_EUNSUPPORTED beyond); exported for unit tests (bit-identical to mmpfn_linear_bf16 +
  * mmpfn_feature_attention_bf16) and timing.
  *   x [n_rows*T][192] bf16, w_qkv [576][192] bf16  ->  att [n_rows*T][192] bf16 */

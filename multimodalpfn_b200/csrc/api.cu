@@ -587,20 +587,20 @@ static int layers_run(const mmpfn_geometry* g, const mmpfn_weights* w, float* st
     const LayerW lw = layer_w(w, l);
     // features: QKV over all tokens, attention per segment (rows of T_i tokens), out-projection + LN over all
     if (phase != 2) {
-      // rows of up to 32 tokens: projection and attention in one kernel per segment (the qkv block stays on chip);
-      // wider rows: one flat projection, then the attention per segment
-      bool fused = feat_fused;
-      for (int i = 0; i < n_seg; ++i) fused = fused && feat_qkv_attn_supported(segs[i].T);
-      if (!fused) {
-        TcGemm a{};
-        a.A = state_b; a.W = lw.fqkv_b; a.M = (int)M; a.N = 3 * kE; a.K = kE; a.epi = TC_EPI_BF16; a.out_bf16 = ws.hid_b;
-        MMPFN_TRY(proj_gemm(a, st));
-      }
+      // rows of up to 64 tokens: projection and attention in one kernel (the qkv block stays on chip); wider rows:
+      // the projection, then the attention.  Per segment either way.
       long long off = 0;
       for (int i = 0; i < n_seg; ++i) {
         const long long m = (long long)segs[i].B * S * segs[i].T;
-        if (fused) MMPFN_TRY(launch_feat_qkv_attn(state_b + off * kE, lw.fqkv_b, m, segs[i].T, ws.att_b + off * kE, st));
-        else MMPFN_TRY(launch_feat_attn_bf16(ws.hid_b + off * 3 * kE, ws.att_b + off * kE, (long long)segs[i].B * S, segs[i].T, st));
+        if (feat_fused && feat_qkv_attn_supported(segs[i].T)) {
+          MMPFN_TRY(launch_feat_qkv_attn(state_b + off * kE, lw.fqkv_b, m, segs[i].T, ws.att_b + off * kE, st));
+        } else {
+          TcGemm a{};
+          a.A = state_b + off * kE; a.W = lw.fqkv_b; a.M = (int)m; a.N = 3 * kE; a.K = kE; a.epi = TC_EPI_BF16;
+          a.out_bf16 = ws.hid_b + off * 3 * kE;
+          MMPFN_TRY(proj_gemm(a, st));
+          MMPFN_TRY(launch_feat_attn_bf16(ws.hid_b + off * 3 * kE, ws.att_b + off * kE, (long long)segs[i].B * S, segs[i].T, st));
+        }
         off += m;
       }
       TcGemm o{};

@@ -124,7 +124,7 @@ int launch_kv_extract_f32(const float* qkv, float* kv, int B, int S, int T, cuda
 // attention between features: qkv [rows = n_seq*T][3*kE] (q|k|v, head-major) -> att [rows][kE]
 int launch_feat_attn_f32(const float* qkv, float* att, long long n_seq, int T, cudaStream_t st);
 int launch_feat_attn_bf16(const uint16_t* qkv, uint16_t* att, long long n_seq, int T, cudaStream_t st);
-// QKV projection + feature attention in one kernel (kernels_featfused.cu); T <= 32
+// QKV projection + feature attention in one kernel (kernels_featfused.cu); T <= 64
 bool feat_qkv_attn_supported(int T);
 int launch_feat_qkv_attn(const uint16_t* x, const uint16_t* w_qkv, long long M, int T, uint16_t* att, cudaStream_t st);
 

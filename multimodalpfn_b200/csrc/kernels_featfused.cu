@@ -9,7 +9,7 @@
 //
 //   * a CTA owns ONE PAIR OF HEADS: its 72 KB slice of W_qkv (q, k and v rows of the two heads) stays resident in
 //     shared memory for the CTA's whole life (the K = 192 projections live on bytes in flight, not on MMA rate:
-//     kernels_rowgemm.cu), and it walks tiles of G = 128 / T whole table rows (G T <= 128 tokens);
+//     kernels_rowgemm.cu), and it walks tiles of G = 128 / T whole table rows (G T <= 128 tokens; T <= 64);
 //   * tcgen05: one 128 x 192 x 192 MMA group per tile into TMEM (accumulators double buffered), A tile by TMA;
 //   * four epilogue warps (thread = token) round the accumulators to bf16 into a shared-memory block of token rows
 //     [q0 q1 k0 k1 v0 v1] (400-byte pitch: conflict-free ldmatrix), head 0's three column blocks first;
@@ -230,7 +230,7 @@ int launch_fused_t(const CUtensorMap& ma, const CUtensorMap& mw, const FusedArgs
 
 }  // namespace
 
-bool feat_qkv_attn_supported(int T) { return T >= 2 && T <= 32; }
+bool feat_qkv_attn_supported(int T) { return T >= 2 && T <= 64; }
 
 // x [M][192] bf16 (M = n_rows * T), w_qkv [576][192] bf16 -> att [M][192] bf16
 int launch_feat_qkv_attn(const uint16_t* x, const uint16_t* w_qkv, long long M, int T, uint16_t* att, cudaStream_t st) {
@@ -262,7 +262,7 @@ int launch_feat_qkv_attn(const uint16_t* x, const uint16_t* w_qkv, long long M, 
   if (per > a.m_tiles) per = a.m_tiles;
   if (per < 1) per = 1;
   a.ctas_per_pair = per;
-  return launch_fused_t<2>(ma, mw, a, per * 3, st);
+  return T <= 32 ? launch_fused_t<2>(ma, mw, a, per * 3, st) : launch_fused_t<4>(ma, mw, a, per * 3, st);
 }
 
 }  // namespace mmpfn

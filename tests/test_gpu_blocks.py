@@ -204,7 +204,8 @@ def test_feature_attention_bf16(n_rows, T):
     assert (att.float() - ref).abs().max().item() < 0.03      # P and the output rounded to bf16, O(1) values
 
 
-@pytest.mark.parametrize("n_rows,T", [(1, 2), (5, 3), (7, 16), (301, 20), (2000, 27), (333, 32), (9200, 27)])
+@pytest.mark.parametrize("n_rows,T", [(1, 2), (5, 3), (7, 16), (301, 20), (2000, 27), (333, 32), (9200, 27), (100, 33), (640, 42), (77, 50),
+                                      (9, 64)])
 def test_feature_qkv_attention_fused(n_rows, T):
     """QKV projection + feature attention in one kernel (csrc/kernels_featfused.cu) against the two-kernel form
     (persistent tcgen05 projection, then the mma.sync attention) on the same operands: the same MMAs in the same
@@ -228,10 +229,10 @@ def test_feature_qkv_attention_fused(n_rows, T):
 
 def test_feature_qkv_attention_fused_rejects_wide_rows():
     lib = _lib.load()
-    x = torch.zeros(66, 192, dtype=torch.bfloat16, device="cuda")
+    x = torch.zeros(130, 192, dtype=torch.bfloat16, device="cuda")
     w = torch.zeros(576, 192, dtype=torch.bfloat16, device="cuda")
-    out = torch.zeros(66, 192, dtype=torch.bfloat16, device="cuda")
-    assert lib.mmpfn_feature_qkv_attention_bf16(x.data_ptr(), w.data_ptr(), 2, 33, out.data_ptr(), _stream()) == -4      # MMPFN_EUNSUPPORTED
+    out = torch.zeros(130, 192, dtype=torch.bfloat16, device="cuda")
+    assert lib.mmpfn_feature_qkv_attention_bf16(x.data_ptr(), w.data_ptr(), 2, 65, out.data_ptr(), _stream()) == -4      # MMPFN_EUNSUPPORTED
 
 
 @pytest.mark.parametrize("mgm,cap,rows,n_tok", [(2, 4, 77, 1), (8, 8, 300, 2), (64, 24, 130, 1)])
