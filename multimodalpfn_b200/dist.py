@@ -324,13 +324,41 @@ class ShardedEngine:
                 flat = t.view(W, -1)
                 dist.all_gather_into_tensor(flat.view(-1), flat[r] if dev.type == "cuda" else flat[r].clone(), group=self.group)
             return (W - 1) * (t.numel() // W)
-        for l in range(L):
-            for st, stb, segs, S_loc, kw in shares:
-                m.layers_run(st, stb, segs, S_loc, None, l, l + 1, phase=1, **kw)
-            for b in bufs:
-                nbytes += gather(b["kg"]) + gather(b["vtg"])
-            for st, stb, segs, S_loc, kw in shares:
-                m.layers_run(st, stb, segs, S_loc, None, l, l + 1, phase=2, **kw)
+        if dev.type == "cuda" and not emulate and len(bufs) > 1:
+            # several estimator groups: group by group, with the all-gathers on a communication stream — the planes
+            # of group g travel while group g+1 runs its row-wise sublayers and while earlier groups attend
+            if self._comm is None:
+                self._comm = torch.cuda.Stream(device=dev)
+            main = torch.cuda.current_stream(dev)
+            st, stb, segs, S_loc, _ = shares[0]
+            parts, off = [], 0
+            for sg in segs:
+                n = sg["B"] * S_loc * sg["T"]
+                parts.append((st[off:off + n], stb[off:off + n]))
+                off += n
+            for l in range(L):
+                landed = []
+                for gi, (sg, (ps, pb)) in enumerate(zip(segs, parts)):
+                    m.layers_run(ps, pb, [sg], S_loc, None, l, l + 1, phase=1, ws_key=f"_group{gi}")
+                    ev = torch.cuda.Event()
+                    ev.record(main)
+                    with torch.cuda.stream(self._comm):
+                        self._comm.wait_event(ev)
+                        nbytes += gather(bufs[gi]["kg"]) + gather(bufs[gi]["vtg"])
+                        done = torch.cuda.Event()
+                        done.record(self._comm)
+                    landed.append(done)
+                for gi, (sg, (ps, pb)) in enumerate(zip(segs, parts)):
+                    main.wait_event(landed[gi])
+                    m.layers_run(ps, pb, [sg], S_loc, None, l, l + 1, phase=2, ws_key=f"_group{gi}")
+        else:
+            for l in range(L):
+                for st, stb, segs, S_loc, kw in shares:
+                    m.layers_run(st, stb, segs, S_loc, None, l, l + 1, phase=1, **kw)
+                for b in bufs:
+                    nbytes += gather(b["kg"]) + gather(b["vtg"])
+                for st, stb, segs, S_loc, kw in shares:
+                    m.layers_run(st, stb, segs, S_loc, None, l, l + 1, phase=2, **kw)
         for b in bufs:
             nbytes += gather(b["ctx"])
         self.exchange = {"collective": "all_gather_into_tensor", "calls_per_step": 2 * L * len(bufs) + len(bufs),
