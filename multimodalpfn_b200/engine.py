@@ -102,6 +102,7 @@ class B200InferenceEngine:
         self._pinned_bufs = {}
         self.multi_group = True                # False: one pass per group (tests compare the two, bit for bit)
         self._stage_event = None
+        self._side = None                      # side stream of the test-row image stem
         self.launches_per_call = None
         if cache_context:
             self._build_contexts()
@@ -186,12 +187,28 @@ class B200InferenceEngine:
                     out[i] = lg[k]
         elif multi:
             tok_tr = tok_te = None
+            join = None
             if img_test_dev is not None:
-                tok_tr, tok_te = self.train_image_tokens(), m.stem_image(img_test_dev)
+                tok_tr = self.train_image_tokens()
+                # the image/text stem of the TEST rows (a dozen small, latency-bound launches) does not depend on the
+                # context build: it runs on a side stream beside the train pass and joins before the test pass
+                dev = m.device
+                main = torch.cuda.current_stream(dev)
+                if self._side is None:
+                    self._side = torch.cuda.Stream(device=dev)
+                self._side.wait_stream(main)
+                with torch.cuda.stream(self._side):
+                    tok_te = m.stem_image(img_test_dev)
+                    join = torch.cuda.Event()
+                    join.record(self._side)
+                if not torch.cuda.is_current_stream_capturing():
+                    tok_te.record_stream(main)
             specs = [dict(X_train=g["X_train"], y_train=g["y_train"], X_all=torch.cat([g["X_train"], Xte], dim=1),
                           img_tok_train=tok_tr, label_stats=g["label_stats"])
                      for g, Xte in zip(self.groups, staged["X_test"])]
             ctxs = m.fit_contexts(specs, nan_flag=flag)
+            if join is not None:
+                torch.cuda.current_stream(m.device).wait_event(join)
             lgs = m.predict_with_contexts(ctxs, staged["X_test"], img_tok_test=tok_te, nan_flag=flag)
             for g, lg in zip(self.groups, lgs):
                 for k, i in enumerate(g["idx"]):
