@@ -187,6 +187,29 @@ def test_model_random_configs_vs_oracle(seed):
         assert np.abs(p - pr).max() <= P_TOL[precision], (precision, mixer, mgm, cap, n_tr, n_te, F, n_tok, n_cls)
 
 
+@pytest.mark.parametrize("n_tr,n_te,F,n_tok", [(2, 1, 1, 0), (3, 2, 2, 1), (5, 1, 3, 2), (49, 1, 1, 1), (17, 130, 63, 0),
+                                               (128, 129, 62, 1)])
+def test_model_extreme_shapes_vs_oracle(n_tr, n_te, F, n_tok):
+    """The smallest contexts the reference accepts (two train rows, one test row, one feature -> T = 2), a key count
+    one past a tile boundary, rows of 32 and 33 / 40 tokens (fused feature kernel on both sides of its m-tile
+    counts), with and without embeddings — CUDA path (fp32 and bf16) vs the oracle."""
+    from multimodalpfn_b200.synth import Geometry, make_state_dict
+    geom = Geometry(mgm_heads=2, cap_heads=4, nlayers=2)
+    sd = make_state_dict(geom, seed=21)
+    rng = np.random.default_rng(n_tr * 1000 + n_te * 10 + F)
+    S = n_tr + n_te
+    X = rng.standard_normal((S, F)).astype(np.float32)
+    img = rng.standard_normal((S, n_tok, 768)).astype(np.float32) if n_tok else None
+    y = (np.arange(n_tr) % 2).astype(np.float32)
+    ref = R.forward_joint(t(X), None if img is None else t(img), t(y), R.as_torch_state_dict(sd), geom, seed=0).numpy()
+    for precision in ("fp32", "bf16"):
+        model = B200PerFeatureTransformer(sd, geom, precision=precision, seed=0)
+        logits = _run_joint(model, X, img, y)
+        assert logits.shape == ref.shape and np.isfinite(logits).all()
+        p, pr = softmax_np(logits[:, :2] / 0.9), softmax_np(ref[:, :2] / 0.9)
+        assert np.abs(p - pr).max() <= P_TOL[precision], (precision, float(np.abs(p - pr).max()))
+
+
 @pytest.mark.parametrize("fit_mode", ["fit_preprocessors", "fit_with_cache"])
 def test_multi_group_pass_equals_per_group(fit_mode):
     """Estimator groups of different token counts through mmpfn_layers_*_multi (flat sublayers launched once
