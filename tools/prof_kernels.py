@@ -1,5 +1,6 @@
 """One launch of each hot kernel at the cfg2 shape (B=4 estimators, 2000 train rows, T=27), for ncu:
-QKV projection, item QKV projection + scatter, output projection + LayerNorm, fused MLP, item attention."""
+QKV projection, fused feature QKV + attention, item QKV projection + scatter, output projection + LayerNorm, fused MLP,
+item attention (5 + 1 launches per round, two rounds)."""
 import os
 import sys
 
@@ -31,6 +32,7 @@ kp = torch.empty_like(q)
 ctx = [torch.empty(B * T * pad * 32, device=dev, dtype=torch.bfloat16) for _ in range(2)]
 for _ in range(2):
     _lib.check(lib.mmpfn_linear_bf16(A.data_ptr(), W.data_ptr(), M, 3 * E, E, 0, O.data_ptr(), st), "qkv")
+    _lib.check(lib.mmpfn_feature_qkv_attention_bf16(A.data_ptr(), W.data_ptr(), B * n, T, xb.data_ptr(), st), "feat_fused")
     _lib.check(lib.mmpfn_item_qkv_bf16(A.data_ptr(), W.data_ptr(), B, n, T, pad, 3, q.data_ptr(), kp.data_ptr(),
                                        vt.data_ptr(), ctx[0].data_ptr(), ctx[1].data_ptr(), st), "item_qkv")
     _lib.check(lib.mmpfn_linear_ln_bf16(A.data_ptr(), W.data_ptr(), M, x.data_ptr(), xb.data_ptr(), st), "out_ln")
