@@ -167,6 +167,7 @@ class ShardedEngine:
         self._gather = None
         self._comm = None
         self._rows = None          # buffers of the row-sharded mode
+        self._side = None          # side stream: stem + embedding of the test rows beside the context build
         self.exchange = None       # filled per call: bytes gathered, for the bench line
         if shard == "rows":
             if not tabular:
@@ -203,12 +204,37 @@ class ShardedEngine:
         G = self._buffers()
         L = m.geom.nlayers
         n_tr = eng.groups[0]["y_train"].shape[1]
-        tok_tr = tok_te = None
-        if staged["img_test"] is not None:
-            tok_tr, tok_te = eng.train_image_tokens(), m.stem_image(staged["img_test"])
+        tok_tr = eng.train_image_tokens() if staged["img_test"] is not None else None
         # stem statistics of every estimator from the train rows + this rank's test chunk (cheap, no exchange)
         stats = [m.stem_tab_fit(torch.cat([g["X_train"], Xte], dim=1), n_tr)
                  for g, Xte in zip(eng.groups, staged["X_test"])]
+        # The image/text stem and the token embedding of this rank's TEST rows (a dozen small launches) do not depend
+        # on the context build: they run on a side stream beside it and join before the first test layer.
+        n_te = staged["X_test"][0].shape[1]
+
+        def embed_test_rows():
+            tok_te = m.stem_image(staged["img_test"]) if staged["img_test"] is not None else None
+            y_nan = torch.full((1, n_te), float("nan"), dtype=torch.float32, device=dev)
+            bufs = m._group_buffers([(len(g["idx"]), n_te, t) for g, t in zip(eng.groups, self.Ts)])
+            for gi, (g, v) in enumerate(zip(eng.groups, bufs[2])):
+                ls = g["label_stats"]
+                m.embed(staged["X_test"][gi], stats[gi], tok_te, y_nan, ls[0], ls[1], m.positional_embeddings(self.Ts[gi] - 1),
+                        B=len(g["idx"]), S=n_te, F=g["F"], x_bstride=n_te * g["F"], y_bstride=0, nan_flag=flag, out=v)
+            return bufs
+        test_ready = None
+        if cuda:
+            main = torch.cuda.current_stream(dev)
+            if self._side is None:
+                self._side = torch.cuda.Stream(device=dev)
+            self._side.wait_stream(main)
+            with torch.cuda.stream(self._side):
+                st2, stb2, views2 = embed_test_rows()
+                test_ready = torch.cuda.Event()
+                test_ready.record(self._side)
+            for tns in (st2, stb2):
+                tns.record_stream(main)
+        else:
+            st2, stb2, views2 = embed_test_rows()
         # ---- 1. context build of the estimators this rank owns, all-gather of layer l under layers l+1.. -------
         owned = plan.owned(self.rank)
         shapes = [(len(pos), n_tr, self.Ts[gi]) for gi, pos in owned]
@@ -242,18 +268,14 @@ class ShardedEngine:
         self.exchange = {"collective": "all_gather_into_tensor", "calls_per_step": L,
                          "bytes_received_per_rank": int(L * (self.world - 1) * plan.chunk), "mode": plan.mode}
         # ---- 2. this rank's test rows against every estimator, reading the gathered buffer in place ------------
-        n_te = staged["X_test"][0].shape[1]
-        y_nan = torch.full((1, n_te), float("nan"), dtype=torch.float32, device=dev)
-        st2, stb2, views2 = m._group_buffers([(len(g["idx"]), n_te, t) for g, t in zip(eng.groups, self.Ts)])
         tsegs = []
-        for gi, (g, v) in enumerate(zip(eng.groups, views2)):
+        for gi, g in enumerate(eng.groups):
             gp = plan.groups[gi]
-            ls = g["label_stats"]
-            m.embed(staged["X_test"][gi], stats[gi], tok_te, y_nan, ls[0], ls[1], m.positional_embeddings(self.Ts[gi] - 1),
-                    B=len(g["idx"]), S=n_te, F=g["F"], x_bstride=n_te * g["F"], y_bstride=0, nan_flag=flag, out=v)
             tsegs.append(dict(B=len(g["idx"]), T=self.Ts[gi], kv=G[0, gp.rank0, gp.offset:gp.offset + gp.block],
                               layer_stride=self.world * plan.chunk, slots=gp.slots, rank_stride=plan.chunk,
                               kv_buffer=G, kv_offset=gp.rank0 * plan.chunk + gp.offset))
+        if test_ready is not None:
+            torch.cuda.current_stream(dev).wait_event(test_ready)
         for l in range(L):
             if cuda:
                 torch.cuda.current_stream(dev).wait_event(events[l])
