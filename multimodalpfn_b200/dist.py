@@ -222,7 +222,7 @@ class ShardedEngine:
                         B=len(g["idx"]), S=n_te, F=g["F"], x_bstride=n_te * g["F"], y_bstride=0, nan_flag=flag, out=v)
             return bufs
         test_ready = None
-        if cuda:
+        if cuda and m.geom.mgm_heads < 32:      # (from 32 MGM heads the stem has a TMA / tcgen05 kernel: keep it in line)
             main = torch.cuda.current_stream(dev)
             if self._side is None:
                 self._side = torch.cuda.Stream(device=dev)

@@ -192,17 +192,22 @@ class B200InferenceEngine:
                 tok_tr = self.train_image_tokens()
                 # the image/text stem of the TEST rows (a dozen small, latency-bound launches) does not depend on the
                 # context build: it runs on a side stream beside the train pass and joins before the test pass
-                dev = m.device
-                main = torch.cuda.current_stream(dev)
-                if self._side is None:
-                    self._side = torch.cuda.Stream(device=dev)
-                self._side.wait_stream(main)
-                with torch.cuda.stream(self._side):
+                # (only the FFMA stem: from 32 MGM heads its gated projection is a TMA / tcgen05 kernel, and layer-type
+                # kernels of two streams must not overlap, include/mmpfn_b200.h)
+                if m.geom.mgm_heads < 32:
+                    dev = m.device
+                    main = torch.cuda.current_stream(dev)
+                    if self._side is None:
+                        self._side = torch.cuda.Stream(device=dev)
+                    self._side.wait_stream(main)
+                    with torch.cuda.stream(self._side):
+                        tok_te = m.stem_image(img_test_dev)
+                        join = torch.cuda.Event()
+                        join.record(self._side)
+                    if not torch.cuda.is_current_stream_capturing():
+                        tok_te.record_stream(main)
+                else:
                     tok_te = m.stem_image(img_test_dev)
-                    join = torch.cuda.Event()
-                    join.record(self._side)
-                if not torch.cuda.is_current_stream_capturing():
-                    tok_te.record_stream(main)
             specs = [dict(X_train=g["X_train"], y_train=g["y_train"], X_all=torch.cat([g["X_train"], Xte], dim=1),
                           img_tok_train=tok_tr, label_stats=g["label_stats"])
                      for g, Xte in zip(self.groups, staged["X_test"])]
