@@ -17,8 +17,8 @@
  *    synchronisation, and returns 0 on success or a negative MMPFN_E* code; mmpfn_last_error()
  *    returns a thread-local message for the last failure;
  *  - one layer pass at a time per device: two mmpfn_layers_* calls must not OVERLAP on different
- *    streams of one device (measured: their results corrupt each other although they share no
- *    buffer and every pair of layer kernels is correct when run concurrently in isolation:
+ *    streams of one device (measured: the fused MLP kernel returns a few wrong rows when other
+ *    compute kernels share the GPU with it for long stretches, although no buffer is shared:
  *    profiles/r02_interleaved_test_layers_experiment.txt).  Stem, decoder and tail calls and
  *    collectives may run beside a layer pass; that is what the engines of this repository do;
  *  - there is NO CPU fallback: on a machine without an sm_100 device every compute entry point

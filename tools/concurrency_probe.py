@@ -105,3 +105,56 @@ for na, nb in itertools.product(a_ops, b_ops):
         bad.append((na, nb, worst))
     print(f"{na:16s} || {nb:16s}: max |concurrent - alone| = {worst:.3e}{flag}", flush=True)
 print("pairs that differ:", bad)
+
+# ---- chains: every stream runs a LAYER-like sequence of launches (many cross-stream alternations per SM) --------------
+chain = ["feat_fused", "out_proj_ln", "item_qkv", "item_attn_train", "mlp", "qkv_proj"]
+chain_b = ["feat_fused", "out_proj_ln", "item_qkv", "item_attn_test", "mlp", "qkv_proj"]
+worst = {}
+for rep in range(8):
+    for ops, names in ((a_ops, chain), (b_ops, chain_b)):
+        for nme in names:
+            ops[nme][2]()
+    torch.cuda.synchronize()
+    for i in range(len(chain)):
+        _lib.check(a_ops[chain[i]][1](s1.cuda_stream), chain[i])
+        _lib.check(b_ops[chain_b[i]][1](s2.cuda_stream), chain_b[i])
+        if rep % 2:      # a second, third round of the non-in-place kernels keeps both streams busy
+            for nme, ops, st_ in ((chain[i], a_ops, s1), (chain_b[i], b_ops, s2)):
+                if nme not in ("out_proj_ln", "mlp"):
+                    _lib.check(ops[nme][1](st_.cuda_stream), nme)
+    torch.cuda.synchronize()
+    for ops, names, refs, tag in ((a_ops, chain, ref_a, "A"), (b_ops, chain_b, ref_b, "B")):
+        for nme in names:
+            for got, ref in zip(ops[nme][0], refs[nme]):
+                d = float((got.float() - ref.float()).abs().max())
+                worst[(tag, nme)] = max(worst.get((tag, nme), 0.0), d)
+print("chains of six launches per stream, 8 repetitions: max |concurrent - alone| per kernel:")
+for k, v in worst.items():
+    print("  ", k, f"{v:.3e}", "" if v == 0.0 else "  <-- DIFFERS")
+
+# ---- is it concurrency or the predecessor on the stream?  chain A alone on one stream ---------------------------------
+for nme in chain:
+    a_ops[nme][2]()
+torch.cuda.synchronize()
+for nme in chain:
+    _lib.check(a_ops[nme][1](s1.cuda_stream), nme)
+torch.cuda.synchronize()
+for nme in chain:
+    d = max(float((got.float() - ref.float()).abs().max()) for got, ref in zip(a_ops[nme][0], ref_a[nme]))
+    print(f"chain A alone on one stream: {nme:16s} max |chain - alone| = {d:.3e}")
+# which rows of the MLP output differ under concurrency
+for rep in range(3):
+    for ops, names in ((a_ops, chain), (b_ops, chain_b)):
+        for nme in names:
+            ops[nme][2]()
+    torch.cuda.synchronize()
+    for i in range(len(chain)):
+        _lib.check(a_ops[chain[i]][1](s1.cuda_stream), chain[i])
+        _lib.check(b_ops[chain_b[i]][1](s2.cuda_stream), chain_b[i])
+    torch.cuda.synchronize()
+    for tag, ops, refs in (("A", a_ops, ref_a), ("B", b_ops, ref_b)):
+        got, ref = ops["mlp"][0][0], refs["mlp"][0]
+        badrows = ((got - ref).abs().amax(1) > 0).nonzero().flatten()
+        tiles = torch.unique(badrows // 128)
+        print(f"rep {rep} stream {tag}: MLP rows that differ: {badrows.numel()} of {got.shape[0]}; tiles (of 128 rows): {tiles[:12].tolist()} ... "
+              f"{tiles.numel()} tiles; tile index mod 148: {torch.unique(tiles % 148)[:10].tolist()}")
