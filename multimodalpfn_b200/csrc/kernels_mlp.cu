@@ -358,7 +358,6 @@ __global__ void __launch_bounds__(F_THREADS, 1) tc_mlp_kernel(const __grid_const
 #pragma unroll
         for (int k = 0; k < 8; ++k) rr[k] = lds128(rrow + ((k ^ rsw) << 4));
         tmem_ld_wait();
-        if (c < F_R_SLOTS) mbar_arrive_warp(&r_empty[slot]);
 #pragma unroll
         for (int k = 0; k < 8; ++k) {
           const float a0 = __uint_as_float(v[4 * k]) + rr[k].x, a1 = __uint_as_float(v[4 * k + 1]) + rr[k].y,
@@ -369,6 +368,11 @@ __global__ void __launch_bounds__(F_THREADS, 1) tc_mlp_kernel(const __grid_const
           v[4 * k + 2] = __float_as_uint(a2); v[4 * k + 3] = __float_as_uint(a3);
         }
         tmem_st32(trow + c * 32, v);
+        // The slot goes back to the producer only HERE, behind the store that consumed the residual values: an arrival
+        // right after the ld.shared instructions were issued does not wait for their data, and the producer's next TMA
+        // load then overwrites the slot under loads still in flight (a few rows per launch read the wrong chunk when
+        // other work delays the warp: profiles/r02_interleaved_test_layers_experiment.txt).
+        if (c < F_R_SLOTS) mbar_arrive_warp(&r_empty[slot]);
       }
       tmem_st_wait();
       const float mean = sum * (1.0f / kE);

@@ -266,7 +266,6 @@ __global__ void __launch_bounds__(R_THREADS, 1) tc_rowgemm_kernel(const __grid_c
 #pragma unroll
           for (int k = 0; k < 8; ++k) rr[k] = lds128(rrow + ((k ^ rsw) << 4));
           tmem_ld_wait();
-          mbar_arrive_warp(&r_empty[slot]);
 #pragma unroll
           for (int k = 0; k < 8; ++k) {
             const float a0 = __uint_as_float(v[4 * k]) + rr[k].x, a1 = __uint_as_float(v[4 * k + 1]) + rr[k].y,
@@ -277,6 +276,9 @@ __global__ void __launch_bounds__(R_THREADS, 1) tc_rowgemm_kernel(const __grid_c
             v[4 * k + 2] = __float_as_uint(a2); v[4 * k + 3] = __float_as_uint(a3);
           }
           tmem_st32(trow + c * 32, v);
+          // (released behind the store that consumed the residual values: an arrival issued right after the ld.shared
+          // instructions does not wait for their data — see kernels_mlp.cu)
+          mbar_arrive_warp(&r_empty[slot]);
         }
         tmem_st_wait();
         const float mean = sum * (1.0f / kE);

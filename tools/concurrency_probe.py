@@ -158,3 +158,13 @@ for rep in range(3):
         tiles = torch.unique(badrows // 128)
         print(f"rep {rep} stream {tag}: MLP rows that differ: {badrows.numel()} of {got.shape[0]}; tiles (of 128 rows): {tiles[:12].tolist()} ... "
               f"{tiles.numel()} tiles; tile index mod 148: {torch.unique(tiles % 148)[:10].tolist()}")
+        gotb, refb = ops["mlp"][0][1], refs["mlp"][1]
+        for tl in tiles[:3].tolist():
+            rows = badrows[(badrows // 128) == tl]
+            r0 = int(rows[0])
+            cols32 = ((got[r0] - ref[r0]).abs() > 0).nonzero().flatten()
+            cols16 = ((gotb[r0].float() - refb[r0].float()).abs() > 0).nonzero().flatten()
+            print(f"     tile {tl}: rows in tile {[int(r) % 128 for r in rows]}; first bad row: {cols32.numel()} of 192 fp32 columns differ "
+                  f"(chunks of 32: {sorted(set((cols32 // 32).tolist()))}), {cols16.numel()} bf16 columns differ; "
+                  f"row mean/std got {float(got[r0].mean()):.3f}/{float(got[r0].std()):.3f} ref {float(ref[r0].mean()):.3f}/{float(ref[r0].std()):.3f}; "
+                  f"max|d| {float((got[r0]-ref[r0]).abs().max()):.3f}")
