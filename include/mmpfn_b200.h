@@ -16,11 +16,9 @@
  *  - every call is asynchronous on `stream` (a cudaStream_t passed as void*), performs no host
  *    synchronisation, and returns 0 on success or a negative MMPFN_E* code; mmpfn_last_error()
  *    returns a thread-local message for the last failure;
- *  - one layer pass at a time per device: two mmpfn_layers_* calls must not OVERLAP on different
- *    streams of one device (measured: the fused MLP kernel returns a few wrong rows when other
- *    compute kernels share the GPU with it for long stretches, although no buffer is shared:
- *    profiles/r02_interleaved_test_layers_experiment.txt).  Stem, decoder and tail calls and
- *    collectives may run beside a layer pass; that is what the engines of this repository do;
+ *  - calls on different streams of one device may overlap (buffers of their own, one workspace per
+ *    call in flight); tools/concurrency_probe.py runs every pair and chains of the layer kernels
+ *    on two streams against their results alone;
  *  - there is NO CPU fallback: on a machine without an sm_100 device every compute entry point
  *    returns MMPFN_ENODEVICE;
  *  - tensors are dense, row-major, innermost dimension last, in the layouts stated per call;

@@ -250,7 +250,19 @@ class ShardedEngine:
             segs.append(dict(B=len(pos), T=self.Ts[gi], kv=G[0, self.rank, gp.offset:gp.offset + gp.block],
                              layer_stride=self.world * plan.chunk, slots=0, rank_stride=0,
                              kv_buffer=G, kv_offset=self.rank * plan.chunk + gp.offset))
-        events = []
+        # this rank's test rows against every estimator read the gathered buffer in place (5-D tensor maps)
+        tsegs = []
+        for gi, g in enumerate(eng.groups):
+            gp = plan.groups[gi]
+            tsegs.append(dict(B=len(g["idx"]), T=self.Ts[gi], kv=G[0, gp.rank0, gp.offset:gp.offset + gp.block],
+                              layer_stride=self.world * plan.chunk, slots=gp.slots, rank_stride=plan.chunk,
+                              kv_buffer=G, kv_offset=gp.rank0 * plan.chunk + gp.offset))
+        # Three streams: the build of layer l (main), its all-gather (communication stream, under the build of layers
+        # l+1..), and — as soon as layer l of every estimator has landed — layer l of the TEST rows (side stream, under
+        # the build of layer l+1: at few estimators per rank both passes are made of short launches that leave SMs idle in
+        # their tails).  The launches are issued in this order, so every stream finds its work in dependency order.
+        interleave = cuda and test_ready is not None
+        landed = []
         for l in range(L):
             if segs:
                 m.layers_run(st, stb, segs, n_tr, None, l, l + 1)
@@ -262,24 +274,22 @@ class ShardedEngine:
                     dist.all_gather_into_tensor(G[l].view(-1), G[l, self.rank], group=self.group)
                     done = torch.cuda.Event()
                     done.record(self._comm)
-                events.append(done)
+                landed.append(done)
+                if interleave:
+                    with torch.cuda.stream(self._side):
+                        self._side.wait_event(done)
+                        m.layers_run(st2, stb2, tsegs, n_te, n_tr, l, l + 1, ws_key="_test")
             else:
                 dist.all_gather_into_tensor(G[l].view(-1), G[l, self.rank].clone(), group=self.group)
         self.exchange = {"collective": "all_gather_into_tensor", "calls_per_step": L,
                          "bytes_received_per_rank": int(L * (self.world - 1) * plan.chunk), "mode": plan.mode}
-        # ---- 2. this rank's test rows against every estimator, reading the gathered buffer in place ------------
-        tsegs = []
-        for gi, g in enumerate(eng.groups):
-            gp = plan.groups[gi]
-            tsegs.append(dict(B=len(g["idx"]), T=self.Ts[gi], kv=G[0, gp.rank0, gp.offset:gp.offset + gp.block],
-                              layer_stride=self.world * plan.chunk, slots=gp.slots, rank_stride=plan.chunk,
-                              kv_buffer=G, kv_offset=gp.rank0 * plan.chunk + gp.offset))
-        if test_ready is not None:
-            torch.cuda.current_stream(dev).wait_event(test_ready)
-        for l in range(L):
-            if cuda:
-                torch.cuda.current_stream(dev).wait_event(events[l])
-            m.layers_run(st2, stb2, tsegs, n_te, n_tr, l, l + 1)
+        if interleave:
+            torch.cuda.current_stream(dev).wait_stream(self._side)
+        else:
+            for l in range(L):
+                if cuda:
+                    torch.cuda.current_stream(dev).wait_event(landed[l])
+                m.layers_run(st2, stb2, tsegs, n_te, n_tr, l, l + 1)
         out = [None] * len(self.members)
         for g, v in zip(eng.groups, views2):
             lg = m.decode(v[0])
