@@ -320,3 +320,20 @@ def test_single_layer_random_shapes(seed):
         e2 = (se[b].cpu() - ref_te).abs().max().item()
         assert e1 < 0.06 and e2 < 0.06, (B, S, T, n_test, e1, e2)
         assert (stb[b].float().cpu() - ref_tr).abs().max().item() < 0.09
+
+
+def test_layer_kernels_on_two_streams():
+    """Every pair of layer kernels, and layer-like chains of six launches, on two streams at once (buffers of their
+    own) against the same kernels run alone: bit-identical.  Regression test of the residual-ring release order of
+    the LayerNorm epilogues (csrc/kernels_mlp.cu, kernels_rowgemm.cu): released before the ld.shared data had
+    arrived, a few rows per launch went wrong under a co-running load — never alone."""
+    import os
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    out = subprocess.run([sys.executable, os.path.join(root, "tools", "concurrency_probe.py")], capture_output=True,
+                         text=True, timeout=600, cwd=root)
+    assert out.returncode == 0, out.stderr[-2000:]
+    assert "pairs that differ: []" in out.stdout, out.stdout[-3000:]
+    assert "DIFFERS" not in out.stdout, out.stdout[-3000:]
+    assert "chains of six launches per stream" in out.stdout
