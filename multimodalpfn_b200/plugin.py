@@ -133,6 +133,7 @@ class B200PluginEngine:
         return self._img_pin.to(self.model.device, non_blocking=True)
 
     def _verify_replay(self, X):
+        import numpy as np
         from . import ref_transform
         from .engine import B200InferenceEngine
         probe = ref_transform.make_probe(X)
@@ -141,6 +142,17 @@ class B200PluginEngine:
                 continue
             if not (ref_transform.verify(pre, fast, X) and ref_transform.verify(pre, fast, probe)):
                 self.replay_state, self.replay_note = "off", f"replay of member {i} differs from the reference's transform"
+                return
+        # ... and through the memo that lets members share equal fitted nodes within one call
+        fasts = [None if m["X_train"] is None else f for m, f in zip(self.members, self._fast)]
+        for table in (X, probe):
+            try:
+                shared = ref_transform.replay_all(fasts, table)
+                refs = [None if f is None else np.asarray(pre.transform(table).X) for pre, f in zip(self.preprocessors, fasts)]
+            except Exception:
+                continue                  # (a table the reference refuses: verified member by member above)
+            if not all(a is None or (a.shape == b.shape and np.array_equal(a, b, equal_nan=True)) for a, b in zip(shared, refs)):
+                self.replay_state, self.replay_note = "off", "shared replay differs from the reference's transform"
                 return
         self._all = B200InferenceEngine(self.model, self.members, self.ref.image_train, cache_context=self._cache_context)
         self._all._img_tok_train = self.stages[0][1].train_image_tokens()
@@ -153,8 +165,9 @@ class B200PluginEngine:
         if X is not None and self.replay_state == "unverified":
             self._verify_replay(X)
         if X is not None and self.replay_state == "on":
-            X_tests = [None if m["X_train"] is None else np.asarray(f(X), dtype=np.float32)
-                       for m, f in zip(self.members, self._fast)]
+            from . import ref_transform
+            X_tests = [None if t is None else np.asarray(t, dtype=np.float32) for t in ref_transform.replay_all(
+                [None if m["X_train"] is None else f for m, f in zip(self.members, self._fast)], X)]
             lg = self._all.logits(X_tests, None, image_dev=image_dev)
             self._all.check_nan()
             for out, cfg in zip(lg, self.ensemble_configs):

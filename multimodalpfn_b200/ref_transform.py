@@ -20,15 +20,57 @@ Nothing here is specific to the GPU path: it is host code that stands before the
 """
 from __future__ import annotations
 
+import hashlib
+
 import numpy as np
 
-__all__ = ["Unsupported", "compile_preprocessor", "make_probe", "verify"]
+__all__ = ["Unsupported", "compile_preprocessor", "replay_all", "make_probe", "verify"]
 
 _FLOATS = (np.dtype(np.float32), np.dtype(np.float64))
 
 
 class Unsupported(Exception):
     """The fitted object tree contains something the replay does not reproduce."""
+
+
+# Ensemble members share fitted state: with the reference's default recipes the four "quantile + SVD" members hold
+# the same fitted QuantileTransformer, scaling chain and OrdinalEncoder (same data, same seeds) and differ only in the SVD
+# basis, category shuffle, fingerprint salt and feature shift.  ``replay_all`` opens a per-call memo: a heavy node whose
+# fitted parameters AND input bytes equal those of an earlier evaluation in the same call returns that result (marked
+# read-only; every consumer here copies before it writes).
+_MEMO = None
+
+
+def _digest(*parts) -> bytes:
+    h = hashlib.blake2b(digest_size=16)
+    for p in parts:
+        if isinstance(p, np.ndarray):
+            h.update(str((p.shape, p.dtype.str)).encode())
+            h.update(np.ascontiguousarray(p).tobytes())
+        elif isinstance(p, bytes):
+            h.update(p)
+        else:
+            h.update(repr(p).encode())
+        h.update(b"|")
+    return h.digest()
+
+
+def _memo(sig: bytes, fn):
+    """``fn`` with the per-call memo in front (key: node signature + the input's shape, dtype and bytes)."""
+    def run(X):
+        memo = _MEMO
+        if memo is None:
+            return fn(X)
+        key = (sig, _digest(X))
+        hit = memo.get(key)
+        if hit is None:
+            hit = fn(X)
+            if isinstance(hit, np.ndarray):
+                hit.setflags(write=False)
+            memo[key] = hit
+        return hit
+    run.signature = sig
+    return run
 
 
 def _float_copy(X):
@@ -57,7 +99,12 @@ def _compile_sk(t):
         func, kw = t.func, dict(t.kw_args or {})
         if func is None:
             return lambda X: X
-        return lambda X: func(X, **kw)
+
+        def run_func(X):
+            return func(X, **kw)
+        if not kw and getattr(func, "__module__", "").endswith("model.preprocessing"):
+            run_func.signature = _digest("func", func.__name__)         # the reference's own pure helpers (_inf_to_nan_func, ...)
+        return run_func
     if name == "Pipeline":
         fs = [_compile_sk(s) for _, s in t.steps]
 
@@ -65,6 +112,9 @@ def _compile_sk(t):
             for f in fs:
                 X = f(X)
             return X
+        sigs = [getattr(f, "signature", None) for f in fs]
+        if len(fs) > 1 and all(sg is not None for sg in sigs):        # a chain of pure fitted nodes: one memo entry for all
+            return _memo(_digest("pipeline", *sigs), run_pipeline)
         return run_pipeline
     if name == "FeatureUnion":
         if t.transformer_weights:
@@ -99,7 +149,7 @@ def _compile_sk(t):
             if np.isinf(Xc).any():        # sklearn's validation (ensure_all_finite="allow-nan") refuses these
                 raise ValueError("Input X contains infinity or a value too large for dtype('float64').")
             return t._transform(Xc, inverse=False)      # sklearn's own per-column interpolation kernel
-        return run_quantile
+        return _memo(_digest("quantile", t.quantiles_, t.references_, t.output_distribution), run_quantile)
     if name == "SimpleImputer":
         stats = np.asarray(t.statistics_, dtype=np.float64)
         mv = t.missing_values
@@ -115,6 +165,7 @@ def _compile_sk(t):
             if mask.any():
                 Xc[mask] = np.broadcast_to(stats.astype(Xc.dtype, copy=False), Xc.shape)[mask]
             return Xc
+        run_impute.signature = _digest("impute", stats)
         return run_impute
     if name == "StandardScaler":
         mean = t.mean_ if t.with_mean else None
@@ -127,6 +178,7 @@ def _compile_sk(t):
             if scale is not None:
                 Xc /= scale
             return Xc
+        run_scale.signature = _digest("scale", "none" if mean is None else mean, "none" if scale is None else scale)
         return run_scale
     if name == "TruncatedSVD":
         comp_t = t.components_.T            # the view sklearn multiplies with (safe_sparse_dot(X, components_.T))
@@ -167,7 +219,7 @@ def _compile_sk(t):
                 col[~hit] = unknown
                 out[:, j] = col
             return out
-        return run_ordinal
+        return _memo(_digest("ordinal", *cats, sorted(missing.items()), unknown, enc_missing, np.dtype(dtype).str), run_ordinal)
     raise Unsupported(name)
 
 
@@ -200,6 +252,8 @@ def _compile_step(step):
 
         def run_encode(X):
             out = f(X)
+            if mappings and not out.flags.writeable:
+                out = out.copy()
             for col, mapping in mappings.items():
                 column = out[:, col]
                 keep = ~np.isnan(column)
@@ -233,6 +287,16 @@ def compile_preprocessor(seq):
             X = f(X)
         return X
     return fast
+
+
+def replay_all(fasts, X):
+    """All members' replays of one table with the shared per-call memo (see ``_memo``) -> list of arrays."""
+    global _MEMO
+    _MEMO = {}
+    try:
+        return [None if f is None else f(X) for f in fasts]
+    finally:
+        _MEMO = None
 
 
 def make_probe(X, seed: int = 0):

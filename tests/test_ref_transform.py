@@ -63,6 +63,55 @@ def test_replay_is_bit_identical_classifier(tmp_path, dataset):
     assert np.array_equal(before, X, equal_nan=True)
 
 
+def test_shared_replay_of_all_members(tmp_path):
+    """``replay_all``: members share equal fitted nodes (quantile transform, scaling chain, ordinal encoder) through a
+    per-call memo.  Same tables as member-by-member, on two different tables in a row (the memo does not outlive a
+    call), inputs untouched, and the memo is actually hit."""
+    import time
+    from multimodalpfn_b200 import ref_transform as RT
+    clf, d = _fitted(tmp_path, "pad_ufes_small", 8)
+    pres = clf.executor_.preprocessors
+    fasts = [RT.compile_preprocessor(p) for p in pres]
+    X1 = _boundary_table(clf, d["X_test"])
+    X2 = RT.make_probe(_boundary_table(clf, d["X_test"][::-1].copy()), seed=3)
+    for X in (X1, X2, X1):
+        before = X.copy()
+        got = RT.replay_all(fasts, X)
+        for pre, g in zip(pres, got):
+            ref = pre.transform(X).X
+            assert g.dtype == ref.dtype and np.array_equal(ref, g, equal_nan=True)
+        assert np.array_equal(before, X, equal_nan=True) and RT._MEMO is None
+    calls = {"n": 0}
+    orig = RT._digest
+
+    def counting(*parts):
+        calls["n"] += 1
+        return orig(*parts)
+    RT._digest = counting
+    try:
+        RT._MEMO = {}
+        for f in fasts:
+            f(X1)
+        entries, lookups = len(RT._MEMO), calls["n"]
+    finally:
+        RT._digest, RT._MEMO = orig, None
+    assert 0 < entries < lookups, (entries, lookups)          # fewer evaluations than lookups: nodes were shared
+    t0 = time.perf_counter()
+    for _ in range(10):
+        RT.replay_all(fasts, X1)
+    t_shared = (time.perf_counter() - t0) / 10
+    t0 = time.perf_counter()
+    for _ in range(10):
+        [f(X1) for f in fasts]
+    t_each = (time.perf_counter() - t0) / 10
+    t0 = time.perf_counter()
+    for _ in range(3):
+        [p.transform(X1) for p in pres]
+    t_ref = (time.perf_counter() - t0) / 3
+    print(f"8 members, {len(X1)} rows: reference transforms {t_ref * 1e3:.1f} ms, replays {t_each * 1e3:.2f} ms, "
+          f"shared replays {t_shared * 1e3:.2f} ms ({entries} memo entries for {lookups} lookups)")
+
+
 def test_replay_refuses_what_the_reference_refuses(tmp_path):
     from multimodalpfn_b200 import ref_transform as RT
     clf, d = _fitted(tmp_path, "tiny", 2)
