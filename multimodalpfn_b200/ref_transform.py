@@ -265,11 +265,12 @@ def _compile_step(step):
 
         def run_fingerprint(X):
             rows = (X + salt) + salt          # the reference hashes row + salt of the table it already salted once
-            h = np.zeros(X.shape[0], dtype=X.dtype)
             raw = np.ascontiguousarray(rows).tobytes()            # the same bytes as row.tobytes(), row by row
             w = rows.shape[1] * rows.dtype.itemsize
-            for i in range(rows.shape[0]):
-                h[i] = hash(raw[i * w:(i + 1) * w]) % _HASH_MOD / _HASH_MOD
+            hs = np.array([hash(raw[i:i + w]) for i in range(0, w * rows.shape[0], w)], dtype=np.int64)
+            # hash % 10**12 / 10**12 as the reference computes it on Python ints: floor modulo (numpy agrees for a positive
+            # modulus), the remainder is below 2**53, so the true division is the same correctly rounded float64 quotient
+            h = ((hs % _HASH_MOD) / _HASH_MOD).astype(X.dtype)
             return np.concatenate([X, h.reshape(-1, 1)], axis=1)
         return run_fingerprint
     raise Unsupported(name)
