@@ -81,20 +81,19 @@ def test_shared_replay_of_all_members(tmp_path):
             ref = pre.transform(X).X
             assert g.dtype == ref.dtype and np.array_equal(ref, g, equal_nan=True)
         assert np.array_equal(before, X, equal_nan=True) and RT._MEMO is None
-    calls = {"n": 0}
-    orig = RT._digest
+    class Counting(dict):
+        lookups = 0
 
-    def counting(*parts):
-        calls["n"] += 1
-        return orig(*parts)
-    RT._digest = counting
+        def get(self, key, default=None):
+            Counting.lookups += 1
+            return dict.get(self, key, default)
     try:
-        RT._MEMO = {}
+        RT._MEMO = Counting()
         for f in fasts:
             f(X1)
-        entries, lookups = len(RT._MEMO), calls["n"]
+        entries, lookups = len(RT._MEMO), Counting.lookups
     finally:
-        RT._digest, RT._MEMO = orig, None
+        RT._MEMO = None
     assert 0 < entries < lookups, (entries, lookups)          # fewer evaluations than lookups: nodes were shared
     t0 = time.perf_counter()
     for _ in range(10):
